@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — MD steps/s of the non-bonded + VelocityVerlet hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+
+A "step" is one VelocityVerlet MD step (kick, drift, neighbour policy, pairwise forces, kick, CM removal)
+of the workload; at N=1 the workload is BASELINE config[1]: the 256 000-atom argon LJ fluid, cubic PBC,
+rc 1.2 nm, Float32 (FCC + jitter, 90 K, dt 2 fs).
+
+  value   device-resident: K steps inside one mb_simulate_vv call on device arrays, CUDA-event timed.
+  e2e     the same metric through the reference-facing C-ABI call with HOST (pinned) buffers: every call
+          uploads coords+velocities, runs `md_steps_per_call` steps and downloads them (what
+          simulate!(sys, sim, n) costs a Molly user whose System lives in host memory).
+  roofline  dominant kernel = brick_force_kernel; algorithmic bytes 36 B/atom/launch (SURVEY.md §8d:
+          read x 12 + params 12 + write F 12) / mean launch time measured with CUDA events by the
+          library's stage timers; peak = MEASURED_PEAKS.json hbm_gbs. The FP32-ALU fraction that actually
+          binds this kernel is reported beside it (`fp32`).
+  cpu_baseline  the oracle's restatement of Molly's multithreaded CPU algorithm (cell list every 10 steps,
+          +0.2 nm buffer, per-thread force copies) on the same workload, bounded sample.
+
+--impl reference times that CPU restatement alone (Julia is not installed, so Molly.jl itself cannot run;
+kind = "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "tests"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import mbhelpers as H  # noqa: E402
+
+METRIC = "md_steps_per_sec"
+UNIT = "steps/s"
+
+
+def workload(name: str, dtype):
+    """Returns (system description, mollyb200 interactions factory, oracle interactions, dt, r_cut, label)."""
+    import mollyb200 as mb
+    from oracle import oracle as o
+    if name == "c2":
+        sd = H.lj_fluid(40, seed=42, dtype=dtype)  # 256 000 atoms, L = 22.977 nm
+        rc = 1.2
+        inters = (mb.LennardJones(cutoff=mb.DistanceCutoff(rc), use_neighbors=True),)
+        ointers = [o.Inter(o.LJ, o.CUT_DISTANCE, rc, use_neighbors=True)]
+        return sd, inters, ointers, 0.002, rc, "256k-atom LJ fluid, cubic PBC, 1.2nm cutoff, Float32"
+    if name == "c4":
+        sd = H.lj_fluid(63, seed=42, dtype=dtype)  # 1 000 188 atoms
+        rc = 1.2
+        inters = (mb.LennardJones(cutoff=mb.DistanceCutoff(rc), use_neighbors=True),)
+        ointers = [o.Inter(o.LJ, o.CUT_DISTANCE, rc, use_neighbors=True)]
+        return sd, inters, ointers, 0.002, rc, "1M-atom LJ fluid, cubic PBC, 1.2nm cutoff, Float32"
+    if name == "c3":
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "6mrr.npz")))
+        box = g["box"]
+        x = g["coords"] - np.floor(g["coords"] / box) * box
+        sd = dict(n=len(x), box=box, coords=x.astype(dtype), velocities=g["velocities_300K"].astype(dtype),
+                  mass=g["mass"], charge=g["charge"], sigma=g["sigma"], eps=g["eps"], excluded=g["excluded"],
+                  special=g["special"])
+        w_lj, w_c = float(g["lj14scale"]), float(g["coulomb14scale"])
+        inters = (mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True, weight_special=w_lj),
+                  mb.CoulombReactionField(dist_cutoff=1.0, use_neighbors=True, weight_special=w_c))
+        ointers = [o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=w_lj, use_neighbors=True),
+                   o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=w_c, use_neighbors=True)]
+        return sd, inters, ointers, 0.0005, 1.0, "6mrr solvated protein (15 954 atoms), LJ+CRF non-bonded only, Float32"
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload_name: str):
+    """DRAM bytes per launch of the force kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", f"force_kernel_{workload_name}.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32):
+    """Molly-algorithm CPU restatement (oracle): list every 10 steps with rc + 0.2 nm, all host threads."""
+    from oracle import oracle as o
+    orc = H.make_oracle(sd, ointers, dtype=dtype)
+    nt = o.max_threads()
+    x, v = sd["coords"].astype(dtype), sd["velocities"].astype(dtype)
+    if warmup > 0:
+        x, v, _ = orc.simulate_vv(x, v, dt, warmup, remove_cm_every=1, r_list=rc + 0.2, nl_every=10, n_threads=nt)
+    t0 = time.perf_counter()
+    orc.simulate_vv(x, v, dt, steps, remove_cm_every=1, r_list=rc + 0.2, nl_every=10, n_threads=nt)
+    t = time.perf_counter() - t0
+    return steps / t, nt, t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4"])
+    ap.add_argument("--r-list", type=float, default=None)
+    ap.add_argument("--rebuild-every", type=int, default=0, help="0 = displacement-triggered (exact)")
+    ap.add_argument("--brick", type=int, nargs=3, default=(0, 0, 0))
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--md-steps-per-call", type=int, default=100)
+    ap.add_argument("--cpu-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+    wl = args.workload or "c2"
+    dtype = np.float32
+
+    # ------------------------------------------------------------------ reference arm (CPU restatement)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sd, inters, ointers, dt, rc, label = workload(wl, dtype)
+        steps = args.steps if args.steps is not None else (10 if wl != "c3" else 100)
+        steps = min(steps, 20 if wl == "c2" else (5 if wl == "c4" else 400))  # bounded sample
+        warm = min(args.warmup if args.warmup is not None else 1, 2)
+        sps, nt, t = run_cpu(sd, ointers, dt, rc, steps, warm)
+        out = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
+               "warmup": warm, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": label, "n_atoms": int(sd["n"]), "dt_ps": dt, "r_cut_nm": rc},
+               "cpu_baseline": {"value": sps, "unit": UNIT, "cores": nt, "kind": "port",
+                                "sample": f"{steps} MD steps of the same workload (Molly CPU algorithm restated in C+OpenMP: "
+                                          f"cell list every 10 steps, r_list = rc+0.2 nm); Julia is not installed"},
+               "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "ns_per_day": sps * dt * 1e3 * 0.0864}
+        print(json.dumps(out))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import mollyb200 as mb
+    if not torch.cuda.is_available() or mb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sd, inters, ointers, dt, rc, label = workload(wl, dtype)
+    n = int(sd["n"])
+    r_list = args.r_list if args.r_list is not None else (rc + 0.1 if wl != "c3" else rc + 0.12)
+    steps = args.steps if args.steps is not None else (1000 if wl != "c4" else 300)
+    warmup = max(args.warmup if args.warmup is not None else 100, 3)
+
+    atoms = mb.atoms_from_arrays(sd["mass"], sd["charge"], sd["sigma"], sd["eps"], dtype)
+    nf = mb.GPUNeighborFinder(dist_cutoff=r_list, excluded_pairs=sd.get("excluded", np.zeros((0, 2), np.int32)) + 1,
+                              special_pairs=sd.get("special", np.zeros((0, 2), np.int32)) + 1, n_steps=args.rebuild_every)
+    dev = torch.device("cuda", local_rank)
+    xs = torch.from_numpy(sd["coords"].astype(dtype)).to(dev).contiguous()
+    vs = torch.from_numpy(sd["velocities"].astype(dtype)).to(dev).contiguous()
+    sysm = mb.System(atoms=atoms, coords=xs, boundary=mb.CubicBoundary(*sd["box"]), velocities=vs, pairwise_inters=inters,
+                     neighbor_finder=nf, dtype=dtype, device=local_rank)
+    sysm.engine()
+    if any(args.brick) or args.lanes:
+        sysm.set_launch_config(tuple(args.brick), args.lanes)
+    sim = mb.VelocityVerlet(dt=dt, remove_CM_motion=1)
+    rng = np.random.default_rng(1234 + rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also builds the neighbour structure and derives capacities)
+    mb.simulate(sysm, sim, warmup, rng=rng)
+    st0 = sysm.stats()
+    # ---- timed device-resident region: exactly `steps` MD steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    mb.simulate(sysm, sim, steps, init_step=warmup, rng=rng)
+    ev1.record()
+    barrier()
+    t_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = sysm.stats()
+    if dist is not None:
+        tt = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms = float(tt.item())
+    value = world * steps / (t_ms * 1e-3)  # replicas: every rank advances its own copy of the workload
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+
+    # ---- stage timers (separate short run so the event records do not perturb the number above)
+    prof_steps = min(200, steps)
+    sysm.set_profiling(True)
+    mb.simulate(sysm, sim, prof_steps, init_step=warmup + steps, rng=rng)
+    stp = sysm.stats()
+    sysm.set_profiling(False)
+    force_us = 1e3 * stp["force_ms"] / max(stp["force_launches"], 1)
+    vv_us = 1e3 * stp["vv_ms"] / max(stp["vv_launches"], 1)
+    rebuilds_prof = stp["n_rebuilds"] - st1["n_rebuilds"]
+    rebuild_us = 1e3 * stp["rebuild_ms"] / max(rebuilds_prof, 1) if rebuilds_prof else None
+
+    # ---- e2e through the C ABI with host (pinned) buffers
+    e2e = None
+    if not args.no_e2e:
+        spc = args.md_steps_per_call
+        hx = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+        hv = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+        hx.copy_(xs.cpu())
+        hv.copy_(vs.cpu())
+        hsys = mb.System(atoms=atoms, coords=hx.numpy(), boundary=mb.CubicBoundary(*sd["box"]), velocities=hv.numpy(),
+                         pairwise_inters=inters, neighbor_finder=nf, dtype=dtype, device=local_rank)
+        hsys.engine()
+        if any(args.brick) or args.lanes:
+            hsys.set_launch_config(tuple(args.brick), args.lanes)
+        ncalls = max(3, steps // spc)
+        mb.simulate(hsys, sim, spc, rng=rng)  # warm-up call (first build)
+        mb.simulate(hsys, sim, spc, init_step=spc, rng=rng)
+        mb.simulate(hsys, sim, spc, init_step=2 * spc, rng=rng)
+        barrier()
+        t0 = time.perf_counter()
+        for c in range(ncalls):
+            mb.simulate(hsys, sim, spc, init_step=(3 + c) * spc, rng=rng)  # H2D + spc steps + D2H, synchronous
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = float(tt.item())
+        e2e = {"value": world * ncalls * spc / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 3 * 4,
+               "d2h_bytes_per_step": 2 * n * 3 * 4, "md_steps_per_call": spc, "calls": ncalls,
+               "note": "one 'step' of the e2e region = one simulate!-style call of md_steps_per_call MD steps with host "
+                       "coords+velocities uploaded and downloaded inside the timed region"}
+        hsys.close()
+
+    # ---- CPU baseline on rank 0 (bounded sample)
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cs = args.cpu_steps or (10 if wl == "c2" else (3 if wl == "c4" else 200))
+        sps, nt, t = run_cpu(sd, ointers, dt, rc, cs, 1)
+        cpu = {"value": sps, "unit": UNIT, "cores": nt, "kind": "port",
+               "sample": f"{cs} MD steps of the same workload in {t:.1f} s (oracle restatement of Molly's threaded CPU path, "
+                         f"cell list every 10 steps, r_list = rc+0.2 nm)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg_bytes = 36.0 * n  # force-only call, f32
+        achieved = alg_bytes / (force_us * 1e-6) / 1e9 if force_us > 0 else None
+        pairs_in_cut = {"c2": 1.955e7, "c4": 7.64e7, "c3": 2.63e6}[wl]
+        flop_per_pair = 42.0 if wl != "c3" else 50.0
+        fp32_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None
+        fp32_ach = pairs_in_cut * flop_per_pair / (force_us * 1e-6) / 1e12 if force_us > 0 else None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "n_atoms": n, "dt_ps": dt, "r_cut_nm": rc, "r_list_nm": r_list,
+                       "rebuild_policy": "displacement-triggered" if args.rebuild_every == 0 else f"every {args.rebuild_every}",
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+                       "brick_dims": st1["brick_dims"], "list_stride": st1["list_stride"], "n_bricks": st1["n_bricks"],
+                       "l2": "not flushed between steps: step k+1 consumes the state step k wrote; per-step working set = "
+                             f"{(st1['n_list_entries'] * 2 + n * 80) / 1e6:.0f} MB (neighbour list + state) vs 126 MB L2"},
+            "ns_per_day": value * dt * 1e3 * 0.0864,
+            "gpu_launches": int(launches),
+            "rebuilds_in_timed_region": int(st1["n_rebuilds"] - st0["n_rebuilds"]),
+            "violations": int(st1["violations"]),
+            "clocks": clocks,
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "kernel": "brick_force_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(wl), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": force_us},
+            "fp32": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak,
+                     "frac": (fp32_ach / fp32_peak) if (fp32_ach and fp32_peak) else None,
+                     "convention": f"{flop_per_pair:.0f} flop per in-cutoff pair x {pairs_in_cut:.3g} pairs (SURVEY.md §8d)",
+                     "pair_interactions_per_s": pairs_in_cut * value / world},
+            "stage_us": {"force": force_us, "vv_kernels_mean": vv_us, "rebuild": rebuild_us,
+                         "rebuilds_during_profile": int(rebuilds_prof), "profile_steps": prof_steps},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    sysm.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+/*
+ * mollyb200.h — C ABI of libmollyb200.so, the B200-native (sm_100a) engine for
+ * Molly.jl's pairwise non-bonded + VelocityVerlet hot path.
+ *
+ * Every entry point is what a Julia `ccall` (or Python ctypes) binds; no C++ or
+ * torch types cross the boundary. Each function cites the reference interface it
+ * replaces (paths relative to the Molly.jl v0.23.3 tree). See INTEGRATION.md
+ * for the Julia-side shim.
+ *
+ * Conventions
+ *  - All functions return an int32 status: 0 = OK, <0 = error; the message is
+ *    available through mb_last_error(). Nothing throws across the boundary
+ *    (the reference raises Julia `error(...)`, e.g. ext/MollyCUDAExt.jl:733-739;
+ *    the shim turns a non-zero status into the same exception).
+ *  - Array arguments may be DEVICE pointers (the Julia shim passes CuPtr) or HOST
+ *    pointers (the Python harness, the e2e benchmark): the library detects which
+ *    with cudaPointerGetAttributes and stages host buffers itself.
+ *  - Element type of coordinate / velocity / force / atom arrays is the
+ *    context's dtype (32 -> float, 64 -> double), matching System{D,AT,T}.
+ *  - Units are Molly's: nm, ps, g/mol, kJ/mol (force kJ mol^-1 nm^-1); the
+ *    accel conversion factor is exactly 1.
+ *  - There is no CPU fallback: without a CUDA device every call fails loudly.
+ */
+#ifndef MOLLYB200_H
+#define MOLLYB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mb_ctx mb_ctx;
+
+/* interaction kinds: src/interactions/lennard_jones.jl:28-35, coulomb.jl:32-70, :698-747, :1320-1394 */
+enum { MB_LJ = 0, MB_COULOMB = 1, MB_CRF = 2, MB_EWALD_REAL = 3 };
+/* cutoffs: src/cutoffs.jl:47-190 */
+enum { MB_CUT_NONE = 0, MB_CUT_DISTANCE = 1, MB_CUT_SHIFTED_POTENTIAL = 2, MB_CUT_SHIFTED_FORCE = 3 };
+/* mixing rules: src/mixing.jl:20-38 */
+enum { MB_MIX_LORENTZ = 0, MB_MIX_GEOMETRIC = 1 };
+
+enum {
+    MB_OK = 0,
+    MB_ERR_INVALID = -1,     /* bad argument / unsupported combination */
+    MB_ERR_CUDA = -2,        /* CUDA runtime error */
+    MB_ERR_CAPACITY = -3,    /* neighbour/halo capacity overflow (reference: tile overflow error, ext:733-739) */
+    MB_ERR_STATE = -4,       /* call order (e.g. forces before atoms were set) */
+    MB_ERR_NOGPU = -5        /* no CUDA device: there is no CPU fallback */
+};
+
+/* POD descriptor of one PairwiseInteraction (fields of the Julia structs). */
+typedef struct {
+    int32_t kind;             /* MB_LJ | MB_COULOMB | MB_CRF | MB_EWALD_REAL */
+    int32_t cutoff_kind;      /* MB_CUT_* (CRF / Ewald carry their own dist_cutoff in r_cut) */
+    double r_cut;             /* inter.cutoff.dist_cutoff or inter.dist_cutoff */
+    double r_act;             /* reserved (dist_activation) */
+    double weight_special;    /* inter.weight_special */
+    double coulomb_const;     /* inter.coulomb_const (coulomb.jl:16) */
+    double solvent_dielectric;/* CRF (coulomb.jl:676); +inf = conducting */
+    double ewald_alpha;       /* CoulombEwald */
+    int32_t sigma_mix;        /* MB_MIX_* for sigma (default Lorentz) */
+    int32_t eps_mix;          /* MB_MIX_* for epsilon (default geometric) */
+    int32_t approx_erfc;      /* reserved */
+    int32_t use_neighbors;    /* inter.use_neighbors */
+} mb_inter_t;
+
+typedef struct {
+    int64_t n_atoms;
+    int64_t n_rebuilds;        /* neighbour-structure rebuilds since context creation */
+    int64_t n_force_evals;
+    int64_t n_steps;           /* VelocityVerlet steps executed */
+    int64_t n_list_entries;    /* full-shell list entries (incl. padding) of the last build */
+    int64_t n_pairs_in_list;   /* full-shell list entries excluding padding */
+    int32_t n_bricks, n_cells[3], brick_dims[3];
+    int32_t halo_capacity, list_stride, max_neighbors, max_halo;
+    int32_t path;              /* 0 = all-pairs kernel, 1 = cell/brick neighbour-list kernel */
+    int32_t violations;        /* fixed-interval policy: steps where an atom moved > skin/2 */
+    double r_list;
+    int64_t kernel_launches;   /* kernels launched by this context since creation */
+    /* device time per category measured with CUDA events on the context's stream while
+     * mb_set_profiling(ctx, 1) is active: force kernel, VelocityVerlet kernels, rebuild pipeline */
+    double force_ms, vv_ms, rebuild_ms;
+    int64_t force_launches, vv_launches, rebuild_launches;
+} mb_stats_t;
+
+const char* mb_last_error(void);
+int mb_device_count(void);
+
+/* Context = what BuffersGPU + GPUNeighborFinder hold in the reference
+ * (src/force.jl:485-522, src/neighbors.jl:104-115). dtype 32|64. cuda_stream may be NULL. */
+int mb_ctx_create(int device, int dtype, void* cuda_stream, mb_ctx** out);
+void mb_ctx_destroy(mb_ctx* ctx);
+
+/* Atoms in Molly's bits layout Atom{Int32,T,T,T,T,T} (src/types.jl:466-475):
+ * {int32 index; int32 atom_type; T mass; T charge; T sigma; T eps; T lambda; int32 alch_role} =
+ * 32 B (f32) / 56 B (f64). Host or device pointer. */
+int mb_set_atoms(mb_ctx* ctx, int64_t n, const void* atoms_aos);
+/* Same information as plain arrays (what the oracle/tests hold). */
+int mb_set_atoms_soa(mb_ctx* ctx, int64_t n, const void* mass, const void* charge, const void* sigma,
+                     const void* eps);
+/* CubicBoundary side lengths (src/spatial.jl:40). */
+int mb_set_box(mb_ctx* ctx, const double side[3]);
+/* sys.pairwise_inters translated to descriptors (dispatch by type in the reference). */
+int mb_set_inters(mb_ctx* ctx, int n_inters, const mb_inter_t* inters);
+/* GPUNeighborFinder sparse metadata (src/neighbors.jl:104-115, :171-195): 1-based pairs, any order,
+ * duplicates allowed; excluded pairs are skipped by every interaction, special pairs are evaluated
+ * with special=true; excluded wins over special. Host pointers. */
+int mb_set_exceptions(mb_ctx* ctx, int64_t n_excl, const int32_t* excl_i, const int32_t* excl_j,
+                      int64_t n_spec, const int32_t* spec_i, const int32_t* spec_j);
+/* Neighbour policy: r_list = finder dist_cutoff (+ buffer); rebuild_every = n_steps of the finder
+ * (src/neighbors.jl:327, :671); 0 = displacement-triggered (exact: rebuild when an atom moved
+ * more than (r_list - max r_cut)/2 since the last build). */
+int mb_set_neighbor_policy(mb_ctx* ctx, double r_list, int rebuild_every);
+
+/* pairwise_forces_loop_gpu! (ext/MollyCUDAExt.jl:845; caller src/force.jl:1228): ADD the pairwise
+ * forces for coords (n x 3, xyz packed) into fs_mat (3 x n column-major == n x 3 packed, original
+ * atom order) and, if non-NULL, dr (x) f into virial (3x3, column-major, type T). */
+int mb_forces(mb_ctx* ctx, const void* coords, void* fs_mat, void* virial, int64_t step_n);
+/* pairwise_pe_loop_gpu! (ext/MollyCUDAExt.jl:936; caller src/energy.jl:427): ADD sum of pair
+ * energies into pe[0] (type T). */
+int mb_energy(mb_ctx* ctx, const void* coords, void* pe, int64_t step_n);
+/* forces + energy in one traversal (TotalEnergyLogger-style callers). Either output may be NULL. */
+int mb_forces_energy(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, void* virial,
+                     int64_t step_n);
+
+/* simulate!(sys, VelocityVerlet(dt, coupling, remove_CM_motion), n_steps) hot loop
+ * (src/simulators.jl:547-668): wrap, [CM removal when init_step==0], neighbours, F0, then n_steps of
+ * kick / drift / wrap / forces / kick / CM removal (every remove_cm_every steps; 0 = never) /
+ * Andersen coupling (prob = dt/tau per atom per step; kT<=0 disables) / neighbour policy.
+ * coords, vels: n x 3, updated in place (coords returned wrapped into [0,L)). */
+typedef struct {
+    double dt;
+    int64_t n_steps;
+    int64_t init_step;        /* simulate!'s init_step; CM motion is removed up front when 0 */
+    int32_t remove_cm_every;  /* VelocityVerlet.remove_CM_motion (default 1) */
+    double andersen_kT;       /* k*T in kJ/mol, <= 0: no thermostat */
+    double andersen_prob;     /* dt / coupling_const */
+    uint64_t rng_ctr1, rng_key; /* the two rand(rng, UInt64) of src/coupling.jl:197-212 */
+} mb_vv_params_t;
+int mb_simulate_vv(mb_ctx* ctx, void* coords, void* vels, const mb_vv_params_t* p);
+
+/* remove_CM_motion! (ext/MollyCUDAExt.jl:2373; src/spatial.jl:901-929) on an n x 3 velocity array. */
+int mb_remove_cm_motion(mb_ctx* ctx, void* vels);
+/* kinetic_energy (src/energy.jl:56-70): writes 1/2 sum m v.v to *ke_host (double, host). */
+int mb_kinetic_energy(mb_ctx* ctx, const void* vels, double* ke_host);
+
+/* find_neighbors(sys, nf, ..., force=true): force a rebuild from coords now (synchronous; also
+ * re-derives capacities). */
+int mb_rebuild_neighbors(mb_ctx* ctx, const void* coords);
+int mb_stats(mb_ctx* ctx, mb_stats_t* host_out);
+int mb_synchronize(mb_ctx* ctx);
+/* Multiply the auto-derived halo/list capacities (after MB_ERR_CAPACITY). */
+int mb_set_capacity_scale(mb_ctx* ctx, double scale);
+/* Tuning overrides (CUDALaunchConfig analogue, src/cuda_config.jl:27-41): brick dims in cells
+ * (0 = auto), lanes per i-atom (4|8|16|32, 0 = auto). */
+int mb_set_launch_config(mb_ctx* ctx, const int32_t brick_dims[3], int32_t lanes_per_atom);
+
+/* Per-kernel-category CUDA-event timing (benchmark_gpu_tiles.jl-style stage timers,
+ * benchmark/gpu_profile_utils.jl:12-18); results through mb_stats. Resets the accumulators. */
+int mb_set_profiling(mb_ctx* ctx, int enable);
+
+/* Spatial decomposition over ranks (one process per GPU): the context owns the atoms whose wrapped
+ * coordinates fall in brick `coord` of grid px*py*pz; halo exchange goes through callbacks the host
+ * runtime provides (NCCL send/recv in the Python driver). */
+typedef struct {
+    int32_t rank, nranks;
+    int32_t grid[3];
+} mb_decomp_t;
+int mb_set_decomposition(mb_ctx* ctx, const mb_decomp_t* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLLYB200_H */

@@ -1,0 +1,431 @@
+"""Host-side mirror of Molly.jl's API for the non-bonded + VelocityVerlet hot path.
+
+Same names and argument meaning as the reference so the parity tests read like the reference's
+own tests (Julia is not available in the build image; the Julia shim that binds the same C ABI is
+julia/MollyB200Ext.jl):
+
+    Atom, CubicBoundary, System                     src/types.jl:466-475, src/spatial.jl:40, src/types.jl:795-979
+    NoCutoff, DistanceCutoff, Shifted*Cutoff        src/cutoffs.jl:47-190
+    LennardJones, Coulomb, CoulombReactionField     src/interactions/lennard_jones.jl:28-35, coulomb.jl:32-70, :698-747
+    GPUNeighborFinder (+ aliases)                   src/neighbors.jl:104-115
+    VelocityVerlet, AndersenThermostat, simulate    src/simulators.jl:287-295, :547-668; src/coupling.jl:184-212
+    forces, forces_virial, potential_energy         src/force.jl:678-720, src/energy.jl:202-248
+    kinetic_energy, temperature, remove_CM_motion   src/energy.jl:44-175, src/spatial.jl:901-929
+
+Everything numerical happens in libmollyb200.so on the GPU; this module only marshals arrays.
+Units are Molly's (nm, ps, g/mol, kJ/mol) with the Unitful wrappers stripped.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import MollyB200Error  # noqa: F401
+
+COULOMB_CONST = 138.93545764  # src/interactions/coulomb.jl:16
+BOLTZMANN_K = 8.31446261815324e-3  # src/units.jl:186-198
+
+
+# ------------------------------------------------------------------------------------------------
+# types
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Atom:
+    index: int = 1
+    atom_type: int = 1
+    mass: float = 1.0
+    charge: float = 0.0
+    sigma: float = 0.0
+    eps: float = 0.0
+    lam: float = 1.0
+    alch_role: int = 0
+
+
+def atom_dtype(dtype) -> np.dtype:
+    """numpy struct dtype with Molly's bits layout Atom{Int32,T,T,T,T,T} (32 B f32 / 56 B f64)."""
+    f = np.dtype(dtype)
+    return np.dtype([("index", np.int32), ("atom_type", np.int32), ("mass", f), ("charge", f), ("sigma", f),
+                     ("eps", f), ("lam", f), ("alch_role", np.int32)], align=True)
+
+
+def atoms_to_array(atoms: Sequence[Atom], dtype) -> np.ndarray:
+    arr = np.zeros(len(atoms), atom_dtype(dtype))
+    for k, a in enumerate(atoms):
+        arr[k] = (a.index, a.atom_type, a.mass, a.charge, a.sigma, a.eps, a.lam, a.alch_role)
+    return arr
+
+
+def atoms_from_arrays(mass, charge, sigma, eps, dtype) -> np.ndarray:
+    n = len(mass)
+    arr = np.zeros(n, atom_dtype(dtype))
+    arr["index"] = np.arange(1, n + 1)
+    arr["atom_type"] = 1
+    arr["mass"], arr["charge"], arr["sigma"], arr["eps"], arr["lam"] = mass, charge, sigma, eps, 1.0
+    return arr
+
+
+@dataclass
+class CubicBoundary:
+    x: float
+    y: Optional[float] = None
+    z: Optional[float] = None
+
+    def __post_init__(self):
+        if self.y is None:
+            self.y = self.x
+        if self.z is None:
+            self.z = self.x
+
+    @property
+    def side_lengths(self):
+        return np.array([self.x, self.y, self.z], np.float64)
+
+
+@dataclass
+class NoCutoff:
+    pass
+
+
+@dataclass
+class DistanceCutoff:
+    dist_cutoff: float
+
+
+@dataclass
+class ShiftedPotentialCutoff:
+    dist_cutoff: float
+
+
+@dataclass
+class ShiftedForceCutoff:
+    dist_cutoff: float
+
+
+def _cutoff_kind(c):
+    if isinstance(c, NoCutoff):
+        return capi.MB_CUT_NONE, 0.0
+    if isinstance(c, DistanceCutoff):
+        return capi.MB_CUT_DISTANCE, c.dist_cutoff
+    if isinstance(c, ShiftedPotentialCutoff):
+        return capi.MB_CUT_SHIFTED_POTENTIAL, c.dist_cutoff
+    if isinstance(c, ShiftedForceCutoff):
+        return capi.MB_CUT_SHIFTED_FORCE, c.dist_cutoff
+    raise TypeError(f"unsupported cutoff {c!r}")
+
+
+@dataclass
+class LennardJones:
+    cutoff: object = field(default_factory=NoCutoff)
+    use_neighbors: bool = False
+    weight_special: float = 1.0
+    sigma_mixing: str = "lorentz"
+    eps_mixing: str = "geometric"
+
+    def descriptor(self):
+        k, rc = _cutoff_kind(self.cutoff)
+        return capi.MBInter(capi.MB_LJ, k, rc, 0.0, self.weight_special, COULOMB_CONST, 1.0, 0.0,
+                            capi.MB_MIX_GEOMETRIC if self.sigma_mixing == "geometric" else capi.MB_MIX_LORENTZ,
+                            capi.MB_MIX_GEOMETRIC if self.eps_mixing == "geometric" else capi.MB_MIX_LORENTZ, 0,
+                            int(self.use_neighbors))
+
+
+@dataclass
+class Coulomb:
+    cutoff: object = field(default_factory=NoCutoff)
+    use_neighbors: bool = False
+    weight_special: float = 1.0
+    coulomb_const: float = COULOMB_CONST
+
+    def descriptor(self):
+        k, rc = _cutoff_kind(self.cutoff)
+        return capi.MBInter(capi.MB_COULOMB, k, rc, 0.0, self.weight_special, self.coulomb_const, 1.0, 0.0, 0, 1, 0,
+                            int(self.use_neighbors))
+
+
+@dataclass
+class CoulombReactionField:
+    dist_cutoff: float
+    solvent_dielectric: float = 78.3  # coulomb.jl:676
+    use_neighbors: bool = False
+    weight_special: float = 1.0
+    coulomb_const: float = COULOMB_CONST
+
+    def descriptor(self):
+        return capi.MBInter(capi.MB_CRF, capi.MB_CUT_DISTANCE, self.dist_cutoff, 0.0, self.weight_special,
+                            self.coulomb_const, self.solvent_dielectric, 0.0, 0, 1, 0, int(self.use_neighbors))
+
+
+@dataclass
+class CoulombEwald:
+    """Real-space part of Ewald/PME (coulomb.jl:1320-1441); alpha = sqrt(-log(2 tol)) / dist_cutoff."""
+    dist_cutoff: float
+    error_tol: float = 5e-4
+    use_neighbors: bool = False
+    weight_special: float = 1.0
+    coulomb_const: float = COULOMB_CONST
+
+    def descriptor(self):
+        alpha = np.sqrt(-np.log(2 * self.error_tol)) / self.dist_cutoff
+        return capi.MBInter(capi.MB_EWALD_REAL, capi.MB_CUT_DISTANCE, self.dist_cutoff, 0.0, self.weight_special,
+                            self.coulomb_const, 1.0, float(alpha), 0, 1, 0, int(self.use_neighbors))
+
+
+def _pairs_from(obj, n, want_true: bool):
+    """Accept a dense (n,n) bool matrix or an (m,2) array of 1-based pairs."""
+    if obj is None:
+        return np.zeros((0, 2), np.int32)
+    a = np.asarray(obj)
+    if a.ndim == 2 and a.shape == (n, n) and a.dtype == np.bool_:
+        m = a if want_true else ~a
+        i, j = np.nonzero(np.triu(m, 1) | np.triu(m.T, 1))
+        return np.stack([i + 1, j + 1], 1).astype(np.int32)
+    return np.ascontiguousarray(a, np.int32).reshape(-1, 2)
+
+
+@dataclass
+class GPUNeighborFinder:
+    """Device neighbour finder. `eligible`/`special` may be dense bool matrices (as in the reference
+    constructor) or `excluded_pairs`/`special_pairs` sparse 1-based (m,2) arrays (neighbors.jl:104-115).
+    n_steps: rebuild interval (reference default 10 CPU / 25 GPU); 0 = displacement-triggered (exact)."""
+    dist_cutoff: float = 0.0
+    eligible: object = None
+    special: object = None
+    excluded_pairs: object = None
+    special_pairs: object = None
+    n_steps: int = 0
+
+
+# the reference's other finders build the same pair set; here they all map to the device cell list
+DistanceNeighborFinder = GPUNeighborFinder
+CellListMapNeighborFinder = GPUNeighborFinder
+TreeNeighborFinder = GPUNeighborFinder
+
+
+@dataclass
+class AndersenThermostat:
+    temperature: float
+    coupling_const: float
+
+
+@dataclass
+class VelocityVerlet:
+    dt: float
+    coupling: object = None
+    remove_CM_motion: int = 1
+
+
+# ------------------------------------------------------------------------------------------------
+# System
+# ------------------------------------------------------------------------------------------------
+class System:
+    """System(atoms, coords, boundary, velocities, pairwise_inters, neighbor_finder) — src/types.jl:795-979.
+
+    coords / velocities are numpy arrays (n,3) of `dtype` (host) or torch CUDA tensors (device); the
+    engine accepts both through the same C entry points.
+    """
+
+    def __init__(self, atoms, coords, boundary, velocities=None, pairwise_inters=(), neighbor_finder=None,
+                 dtype=np.float32, device: int = 0, k=BOLTZMANN_K):
+        self.dtype = np.dtype(dtype)
+        if isinstance(atoms, np.ndarray) and atoms.dtype.names:
+            self.atoms = np.ascontiguousarray(atoms.astype(atom_dtype(self.dtype)))
+        else:
+            self.atoms = atoms_to_array(atoms, self.dtype)
+        self.n = len(self.atoms)
+        self.boundary = boundary
+        self.coords = self._as_state(coords)
+        self.velocities = self._as_state(velocities if velocities is not None else np.zeros((self.n, 3)))
+        self.pairwise_inters = tuple(pairwise_inters)
+        self.neighbor_finder = neighbor_finder
+        self.device = device
+        self.k = k
+        self._ctx = None
+
+    def _as_state(self, a):
+        if hasattr(a, "data_ptr"):  # torch tensor (device resident)
+            return a
+        return np.ascontiguousarray(np.asarray(a, self.dtype).reshape(self.n, 3))
+
+    @property
+    def masses(self):
+        return self.atoms["mass"].astype(np.float64)
+
+    # ---- engine context ------------------------------------------------------------------------
+    def engine(self):
+        if self._ctx is None:
+            L = capi.load()
+            ctx = C.c_void_p()
+            capi.check(L.mb_ctx_create(self.device, 32 if self.dtype == np.float32 else 64, None, C.byref(ctx)))
+            self._ctx = ctx
+            self._L = L
+            self._configure()
+        return self._ctx
+
+    def _configure(self):
+        L, ctx = self._L, self._ctx
+        capi.check(L.mb_set_atoms(ctx, self.n, self.atoms.ctypes.data))
+        side = (C.c_double * 3)(*self.boundary.side_lengths)
+        capi.check(L.mb_set_box(ctx, side))
+        descs = [it.descriptor() for it in self.pairwise_inters]
+        arr = (capi.MBInter * max(1, len(descs)))(*descs)
+        capi.check(L.mb_set_inters(ctx, len(descs), arr))
+        nf = self.neighbor_finder
+        if nf is not None:
+            if nf.excluded_pairs is not None:
+                ex = _pairs_from(nf.excluded_pairs, self.n, want_true=True)
+            else:
+                ex = _pairs_from(nf.eligible, self.n, want_true=False)
+            sp = _pairs_from(nf.special_pairs if nf.special_pairs is not None else nf.special, self.n, want_true=True)
+            ei, ej = np.ascontiguousarray(ex[:, 0]), np.ascontiguousarray(ex[:, 1])
+            si, sj = np.ascontiguousarray(sp[:, 0]), np.ascontiguousarray(sp[:, 1])
+            self._keep = (ei, ej, si, sj)
+            capi.check(L.mb_set_exceptions(ctx, len(ei), ei.ctypes.data, ej.ctypes.data, len(si), si.ctypes.data,
+                                           sj.ctypes.data))
+            capi.check(L.mb_set_neighbor_policy(ctx, float(nf.dist_cutoff), int(nf.n_steps)))
+
+    def close(self):
+        if self._ctx is not None:
+            self._L.mb_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self) -> dict:
+        st = capi.MBStats()
+        capi.check(self._L.mb_stats(self.engine(), C.byref(st)))
+        out = {}
+        for name, _ in capi.MBStats._fields_:
+            v = getattr(st, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+    def set_profiling(self, enable: bool):
+        capi.check(self._L.mb_set_profiling(self.engine(), int(enable)))
+
+    def set_launch_config(self, brick_dims=(0, 0, 0), lanes_per_atom=0):
+        bd = (C.c_int32 * 3)(*brick_dims)
+        capi.check(self._L.mb_set_launch_config(self.engine(), bd, lanes_per_atom))
+
+
+def _ptr(a):
+    return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+
+
+# ------------------------------------------------------------------------------------------------
+# functions
+# ------------------------------------------------------------------------------------------------
+def forces(sys: System, neighbors=None, step_n: int = 0) -> np.ndarray:
+    """forces(sys[, neighbors, step_n]) — src/force.jl:678-687. Returns (n,3) in kJ mol^-1 nm^-1."""
+    ctx = sys.engine()
+    fs = np.zeros((sys.n, 3), sys.dtype)
+    capi.check(sys._L.mb_forces(ctx, _ptr(sys.coords), fs.ctypes.data, None, step_n))
+    return fs
+
+
+def forces_virial(sys: System, neighbors=None, step_n: int = 0):
+    """forces_virial — src/force.jl:703-720. Returns (forces, virial 3x3)."""
+    ctx = sys.engine()
+    fs = np.zeros((sys.n, 3), sys.dtype)
+    vir = np.zeros(9, sys.dtype)
+    capi.check(sys._L.mb_forces(ctx, _ptr(sys.coords), fs.ctypes.data, vir.ctypes.data, step_n))
+    return fs, vir.reshape(3, 3).T.copy()
+
+
+def potential_energy(sys: System, neighbors=None, step_n: int = 0) -> float:
+    """potential_energy(sys[, neighbors, step_n]) — src/energy.jl:202-248 (pairwise part)."""
+    ctx = sys.engine()
+    pe = np.zeros(1, sys.dtype)
+    capi.check(sys._L.mb_energy(ctx, _ptr(sys.coords), pe.ctypes.data, step_n))
+    return float(pe[0])
+
+
+def forces_energy(sys: System, step_n: int = 0):
+    ctx = sys.engine()
+    fs = np.zeros((sys.n, 3), sys.dtype)
+    pe = np.zeros(1, sys.dtype)
+    capi.check(sys._L.mb_forces_energy(ctx, _ptr(sys.coords), fs.ctypes.data, pe.ctypes.data, None, step_n))
+    return fs, float(pe[0])
+
+
+def find_neighbors(sys: System, *args, **kwargs):
+    """find_neighbors(sys, nf::GPUNeighborFinder, ...) = nothing in the reference (neighbors.jl:364);
+    here it forces a device rebuild and returns None."""
+    capi.check(sys._L.mb_rebuild_neighbors(sys.engine(), _ptr(sys.coords)))
+    return None
+
+
+def simulate(sys: System, sim: VelocityVerlet, n_steps: int, init_step: int = 0, rng=None, max_retries: int = 2):
+    """simulate!(sys, sim::VelocityVerlet, n_steps) — src/simulators.jl:547-668. Mutates sys.coords / velocities."""
+    ctx = sys.engine()
+    p = capi.MBVVParams()
+    p.dt = float(sim.dt)
+    p.n_steps = int(n_steps)
+    p.init_step = int(init_step)
+    p.remove_cm_every = int(sim.remove_CM_motion)
+    p.andersen_kT = 0.0
+    p.andersen_prob = 0.0
+    couplings = sim.coupling if isinstance(sim.coupling, (tuple, list)) else ((sim.coupling,) if sim.coupling else ())
+    for c in couplings:
+        if isinstance(c, AndersenThermostat):
+            p.andersen_kT = sys.k * c.temperature
+            p.andersen_prob = sim.dt / c.coupling_const
+        else:
+            raise TypeError(f"unsupported coupling {c!r} (the stock Molly path handles it)")
+    rng = rng or np.random.default_rng()
+    p.rng_ctr1 = int(rng.integers(0, 2 ** 63))
+    p.rng_key = int(rng.integers(0, 2 ** 63))
+    host = not hasattr(sys.coords, "data_ptr")
+    backup = (sys.coords.copy(), sys.velocities.copy()) if host else None
+    scale = 1.0
+    for attempt in range(max_retries + 1):
+        rc = sys._L.mb_simulate_vv(ctx, _ptr(sys.coords), _ptr(sys.velocities), C.byref(p))
+        if rc == capi.MB_ERR_CAPACITY and backup is not None and attempt < max_retries:
+            sys.coords[...], sys.velocities[...] = backup
+            scale *= 2.0
+            capi.check(sys._L.mb_set_capacity_scale(ctx, scale))
+            continue
+        capi.check(rc)
+        break
+    return sys
+
+
+def kinetic_energy(sys: System) -> float:
+    out = C.c_double(0.0)
+    capi.check(sys._L.mb_kinetic_energy(sys.engine(), _ptr(sys.velocities), C.byref(out)))
+    return out.value
+
+
+def temperature(sys: System) -> float:
+    """src/energy.jl:158-175 with df = 3N - 3 for a periodic 3-D box."""
+    df = 3 * sys.n - 3
+    return 2.0 * kinetic_energy(sys) / (df * sys.k)
+
+
+def remove_CM_motion(sys: System):
+    capi.check(sys._L.mb_remove_cm_motion(sys.engine(), _ptr(sys.velocities)))
+    return sys
+
+
+def random_velocities(sys: System, temp: float, rng=None) -> np.ndarray:
+    """Maxwell-Boltzmann velocities (src/spatial.jl:803-831); host-side setup helper."""
+    rng = rng or np.random.default_rng()
+    sd = np.sqrt(sys.k * temp / np.maximum(sys.masses, 1e-300))
+    return (rng.standard_normal((sys.n, 3)) * sd[:, None]).astype(sys.dtype)
+
+
+def wrap_coords(coords, boundary: CubicBoundary):
+    """wrap_coords — src/spatial.jl:573-586 (host helper for test set-up)."""
+    L = boundary.side_lengths.astype(coords.dtype)
+    return coords - np.floor(coords / L) * L
+
+
+def device_count() -> int:
+    return int(capi.load().mb_device_count())

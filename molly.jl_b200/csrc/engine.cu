@@ -1,0 +1,1159 @@
+// engine.cu — host side of libmollyb200: context, parameter digestion, rebuild pipeline driver,
+// kernel dispatch and the C ABI declared in include/mollyb200.h.
+//
+// There is deliberately no CPU code path: every entry point needs a CUDA device.
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <type_traits>
+
+#include "../../include/mollyb200.h"
+#include "cells.cuh"
+#include "common.cuh"
+#include "force.cuh"
+#include "pair.cuh"
+#include "vv.cuh"
+
+namespace mb {
+
+static thread_local std::string g_last_error;
+static int set_error(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define MB_CUDA(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t err__ = (call);                                                                    \
+        if (err__ != cudaSuccess) {                                                                    \
+            return set_error(MB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__) + " (" + \
+                                              __FILE__ + ":" + std::to_string(__LINE__) + ")");        \
+        }                                                                                              \
+    } while (0)
+#define MB_TRY(expr)                 \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != MB_OK) return rc__; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t ensure(size_t nbytes) {
+        if (nbytes <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, nbytes);
+        if (e == cudaSuccess) bytes = nbytes;
+        return e;
+    }
+    template <typename U>
+    U* as() const {
+        return reinterpret_cast<U*>(p);
+    }
+};
+
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Optional per-category device timing with CUDA events on the engine's stream (mb_set_profiling).
+struct Prof {
+    enum { FORCE = 0, VV = 1, REBUILD = 2, NCAT = 3 };
+    bool enabled = false;
+    cudaStream_t stream = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[NCAT];
+    size_t used[NCAT] = {0, 0, 0};
+    double ms[NCAT] = {0, 0, 0};
+    long long count[NCAT] = {0, 0, 0};
+    ~Prof() {
+        for (int c = 0; c < NCAT; c++)
+            for (auto& p : ev[c]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    }
+    void begin(int c) {
+        if (!enabled) return;
+        if (used[c] == ev[c].size()) {
+            if (ev[c].size() >= 8192) { collect(); }
+            if (used[c] == ev[c].size()) {
+                cudaEvent_t a, b;
+                cudaEventCreate(&a);
+                cudaEventCreate(&b);
+                ev[c].emplace_back(a, b);
+            }
+        }
+        cudaEventRecord(ev[c][used[c]].first, stream);
+    }
+    void end(int c) {
+        if (!enabled) return;
+        cudaEventRecord(ev[c][used[c]].second, stream);
+        used[c]++;
+    }
+    void collect() {
+        cudaStreamSynchronize(stream);
+        for (int c = 0; c < NCAT; c++) {
+            for (size_t k = 0; k < used[c]; k++) {
+                float t = 0;
+                if (cudaEventElapsedTime(&t, ev[c][k].first, ev[c][k].second) == cudaSuccess) { ms[c] += t; count[c]++; }
+            }
+            used[c] = 0;
+        }
+    }
+    void reset() {
+        collect();
+        for (int c = 0; c < NCAT; c++) { ms[c] = 0; count[c] = 0; }
+    }
+};
+
+class EngineBase {
+   public:
+    virtual ~EngineBase() {}
+    virtual int set_atoms_aos(int64_t n, const void* aos) = 0;
+    virtual int set_atoms_soa(int64_t n, const void* mass, const void* charge, const void* sigma, const void* eps) = 0;
+    virtual int set_box(const double side[3]) = 0;
+    virtual int set_inters(int n, const mb_inter_t* in) = 0;
+    virtual int set_exceptions(int64_t ne, const int32_t* ei, const int32_t* ej, int64_t ns, const int32_t* si,
+                               const int32_t* sj) = 0;
+    virtual int set_neighbor_policy(double r_list, int rebuild_every) = 0;
+    virtual int forces_energy(const void* coords, void* fs, void* pe, void* vir, int64_t step_n) = 0;
+    virtual int simulate_vv(void* coords, void* vels, const mb_vv_params_t* p) = 0;
+    virtual int remove_cm(void* vels) = 0;
+    virtual int kinetic_energy(const void* vels, double* out) = 0;
+    virtual int rebuild(const void* coords) = 0;
+    virtual int stats(mb_stats_t* out) = 0;
+    virtual int synchronize() = 0;
+    virtual int set_capacity_scale(double s) = 0;
+    virtual int set_launch_config(const int32_t bd[3], int32_t lpa) = 0;
+    virtual int set_profiling(int enable) = 0;
+};
+
+template <typename T>
+class Engine : public EngineBase {
+    using T4 = typename VT<T>::T4;
+    using T2 = typename VT<T>::T2;
+
+   public:
+    Engine(int device, cudaStream_t stream) : device_(device), stream_(stream) {
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, device);
+        sm_count_ = prop.multiProcessorCount;
+        smem_optin_ = prop.sharedMemPerBlockOptin;
+        for (int d = 0; d < 3; d++) box_[d] = 0;
+        prof_.stream = stream;
+    }
+    ~Engine() override {}
+
+    // ------------------------------------------------------------------------------------------
+    int set_atoms_aos(int64_t n, const void* aos) override {
+        if (n <= 0 || !aos) return set_error(MB_ERR_INVALID, "mb_set_atoms: n <= 0 or null atoms");
+        // Atom{Int32,T,T,T,T,T}: int32 index, int32 atom_type, T mass, T charge, T sigma, T eps, T lambda, int32 role
+        const size_t rec = (sizeof(T) == 4) ? 32 : 56;
+        std::vector<unsigned char> host((size_t)n * rec);
+        MB_CUDA(cudaMemcpy(host.data(), aos, host.size(), cudaMemcpyDefault));
+        h_mass_.resize(n); h_charge_.resize(n); h_sigma_.resize(n); h_eps_.resize(n);
+        for (int64_t i = 0; i < n; i++) {
+            const unsigned char* r = host.data() + (size_t)i * rec;
+            T vals[5];
+            memcpy(vals, r + 8, 5 * sizeof(T));
+            h_mass_[i] = vals[0];
+            h_charge_[i] = vals[1];
+            h_sigma_[i] = vals[2];
+            h_eps_[i] = (vals[4] == (T)0) ? (T)0 : vals[3];  // lambda == 0 -> LJ zero shortcut (mixing.jl:7-11)
+        }
+        n_ = n;
+        dirty_ = true;
+        return MB_OK;
+    }
+    int set_atoms_soa(int64_t n, const void* mass, const void* charge, const void* sigma, const void* eps) override {
+        if (n <= 0 || !mass || !charge || !sigma || !eps)
+            return set_error(MB_ERR_INVALID, "mb_set_atoms_soa: n <= 0 or null array");
+        h_mass_.resize(n); h_charge_.resize(n); h_sigma_.resize(n); h_eps_.resize(n);
+        MB_CUDA(cudaMemcpy(h_mass_.data(), mass, n * sizeof(T), cudaMemcpyDefault));
+        MB_CUDA(cudaMemcpy(h_charge_.data(), charge, n * sizeof(T), cudaMemcpyDefault));
+        MB_CUDA(cudaMemcpy(h_sigma_.data(), sigma, n * sizeof(T), cudaMemcpyDefault));
+        MB_CUDA(cudaMemcpy(h_eps_.data(), eps, n * sizeof(T), cudaMemcpyDefault));
+        n_ = n;
+        dirty_ = true;
+        return MB_OK;
+    }
+    int set_box(const double side[3]) override {
+        for (int d = 0; d < 3; d++) {
+            if (!(side[d] > 0) || std::isinf(side[d]))
+                return set_error(MB_ERR_INVALID, "mb_set_box: side lengths must be finite and > 0 (CubicBoundary)");
+            box_[d] = side[d];
+        }
+        dirty_ = true;
+        return MB_OK;
+    }
+    int set_inters(int n, const mb_inter_t* in) override {
+        if (n < 0 || (n > 0 && !in)) return set_error(MB_ERR_INVALID, "mb_set_inters: bad arguments");
+        int n_lj = 0, n_c = 0;
+        for (int k = 0; k < n; k++) {
+            if (in[k].kind == MB_LJ) n_lj++;
+            else if (in[k].kind == MB_COULOMB || in[k].kind == MB_CRF || in[k].kind == MB_EWALD_REAL) n_c++;
+            else return set_error(MB_ERR_INVALID, "mb_set_inters: unknown interaction kind");
+            if (in[k].cutoff_kind < MB_CUT_NONE || in[k].cutoff_kind > MB_CUT_SHIFTED_FORCE)
+                return set_error(MB_ERR_INVALID, "mb_set_inters: unsupported cutoff kind");
+            if (in[k].kind == MB_LJ && in[k].eps_mix != MB_MIX_GEOMETRIC)
+                return set_error(MB_ERR_INVALID, "mb_set_inters: only geometric epsilon mixing is supported");
+        }
+        if (n_lj > 1 || n_c > 1)
+            return set_error(MB_ERR_INVALID, "mb_set_inters: at most one LJ and one Coulomb-family interaction");
+        inters_.assign(in, in + n);
+        dirty_ = true;
+        return MB_OK;
+    }
+    int set_exceptions(int64_t ne, const int32_t* ei, const int32_t* ej, int64_t ns, const int32_t* si,
+                       const int32_t* sj) override {
+        if (n_ <= 0) return set_error(MB_ERR_STATE, "mb_set_exceptions: set atoms first");
+        auto build = [&](int64_t m, const int32_t* a, const int32_t* b, std::vector<int>& ptr, std::vector<int>& idx,
+                         const std::vector<int>* skip_ptr, const std::vector<int>* skip_idx) -> int {
+            std::vector<std::pair<int, int>> pr;
+            pr.reserve(2 * m);
+            for (int64_t k = 0; k < m; k++) {
+                int i = a[k] - 1, j = b[k] - 1;  // 1-based in, 0-based inside
+                if (i < 0 || j < 0 || i >= n_ || j >= n_)
+                    return set_error(MB_ERR_INVALID, "mb_set_exceptions: index out of bounds");
+                if (i == j) continue;
+                if (skip_ptr && !skip_ptr->empty()) {
+                    bool ex = false;
+                    for (int q = (*skip_ptr)[i]; q < (*skip_ptr)[i + 1]; q++) ex |= ((*skip_idx)[q] == j);
+                    if (ex) continue;  // excluded wins over special
+                }
+                pr.emplace_back(i, j);
+                pr.emplace_back(j, i);
+            }
+            std::sort(pr.begin(), pr.end());
+            pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
+            ptr.assign(n_ + 1, 0);
+            idx.resize(pr.size());
+            for (auto& p : pr) ptr[p.first + 1]++;
+            for (int64_t i = 0; i < n_; i++) ptr[i + 1] += ptr[i];
+            for (size_t k = 0; k < pr.size(); k++) idx[k] = pr[k].second;
+            return MB_OK;
+        };
+        MB_TRY(build(ne, ei, ej, ex_ptr_, ex_idx_, nullptr, nullptr));
+        MB_TRY(build(ns, si, sj, sp_ptr_, sp_idx_, &ex_ptr_, &ex_idx_));
+        if (ex_idx_.empty()) ex_ptr_.clear();
+        if (sp_idx_.empty()) sp_ptr_.clear();
+        dirty_ = true;
+        return MB_OK;
+    }
+    int set_neighbor_policy(double r_list, int rebuild_every) override {
+        if (r_list < 0 || rebuild_every < 0) return set_error(MB_ERR_INVALID, "mb_set_neighbor_policy: negative value");
+        r_list_ = r_list;
+        rebuild_every_ = rebuild_every;
+        dirty_ = true;
+        return MB_OK;
+    }
+    int set_capacity_scale(double s) override {
+        if (!(s >= 1.0)) return set_error(MB_ERR_INVALID, "capacity scale must be >= 1");
+        cap_scale_ = s;
+        have_list_ = false;
+        return MB_OK;
+    }
+    int set_launch_config(const int32_t bd[3], int32_t lpa) override {
+        for (int d = 0; d < 3; d++) {
+            if (bd[d] < 0 || bd[d] > 8) return set_error(MB_ERR_INVALID, "brick dims must be in 0..8");
+            user_b_[d] = bd[d];
+        }
+        if (!(lpa == 0 || lpa == 4 || lpa == 8 || lpa == 16 || lpa == 32))
+            return set_error(MB_ERR_INVALID, "lanes_per_atom must be 0, 4, 8, 16 or 32");
+        lpa_ = lpa ? lpa : 8;
+        have_list_ = false;
+        dirty_ = true;
+        return MB_OK;
+    }
+    int set_profiling(int enable) override {
+        prof_.reset();
+        prof_.enabled = enable != 0;
+        return MB_OK;
+    }
+    int synchronize() override {
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        return MB_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // digest parameters -> kernel constants, allocate per-atom state
+    int prepare() {
+        if (!dirty_) return MB_OK;
+        if (n_ <= 0) return set_error(MB_ERR_STATE, "atoms not set");
+        if (!(box_[0] > 0)) return set_error(MB_ERR_STATE, "box not set");
+        if (n_ > 2000000000LL) return set_error(MB_ERR_INVALID, "too many atoms");
+        memset(&P_, 0, sizeof(P_));
+        const double inf = std::numeric_limits<double>::infinity();
+        bool all_nl = !inters_.empty();
+        double max_rc = 0;
+        bool any_nocut_nl = false;
+        for (auto& in : inters_) {
+            if (!in.use_neighbors) all_nl = false;
+            if (in.cutoff_kind != MB_CUT_NONE || in.kind == MB_CRF || in.kind == MB_EWALD_REAL)
+                max_rc = std::max(max_rc, in.r_cut);
+            else if (in.use_neighbors)
+                any_nocut_nl = true;
+        }
+        const double min_box = std::min(box_[0], std::min(box_[1], box_[2]));
+        path_ = (all_nl && r_list_ > 0 && min_box >= 2.5 * r_list_ && n_ >= 64) ? 1 : 0;
+        if (path_ == 1 && max_rc > r_list_)
+            return set_error(MB_ERR_INVALID, "neighbour list radius is smaller than an interaction cutoff");
+        skin_ = (path_ == 1) ? (any_nocut_nl ? 0.0 : r_list_ - max_rc) : 0.0;
+        P_.has_lj = 0;
+        P_.coul_kind = COUL_NONE;
+        P_.lj_rc2 = (T)0;
+        P_.c_rc2 = (T)0;
+        shift_ = false;
+        bool geo_sigma = false;
+        for (auto& in : inters_) {
+            // effective cutoff: NoCutoff with a neighbour list -> the finder radius (ext/MollyCUDAExt.jl:1691)
+            double rc = inf;
+            int ck = in.cutoff_kind;
+            if (in.kind == MB_CRF || in.kind == MB_EWALD_REAL) {
+                rc = in.r_cut;
+                ck = MB_CUT_DISTANCE;
+            } else if (ck != MB_CUT_NONE) {
+                rc = in.r_cut;
+            } else if (in.use_neighbors && r_list_ > 0) {
+                rc = r_list_;
+            }
+            if (ck >= MB_CUT_SHIFTED_POTENTIAL) shift_ = true;
+            if (in.kind == MB_LJ) {
+                P_.has_lj = 1;
+                P_.lj_cut_kind = ck;
+                P_.lj_rc = (T)rc; P_.lj_rc2 = (T)(rc * rc); P_.lj_inv_rc = (T)(1.0 / rc); P_.lj_inv_rc2 = (T)(1.0 / (rc * rc));
+                P_.lj_w14 = (T)in.weight_special;
+                geo_sigma = (in.sigma_mix == MB_MIX_GEOMETRIC);
+            } else {
+                P_.coul_kind = (in.kind == MB_COULOMB) ? COUL_PLAIN : (in.kind == MB_CRF ? COUL_CRF : COUL_EWALD);
+                P_.coul_cut_kind = ck;
+                P_.c_rc = (T)rc; P_.c_rc2 = (T)(rc * rc); P_.c_inv_rc = (T)(1.0 / rc); P_.c_inv_rc2 = (T)(1.0 / (rc * rc));
+                P_.ke = (T)in.coulomb_const;
+                P_.c_w14 = (T)in.weight_special;
+                P_.alpha = (T)in.ewald_alpha;
+                if (in.kind == MB_CRF) {
+                    double e = in.solvent_dielectric;
+                    double krf, crf;
+                    if (std::isinf(e)) { krf = 1.0 / (2.0 * rc * rc * rc); crf = 3.0 / (2.0 * rc); }
+                    else { krf = (1.0 / (rc * rc * rc)) * (e - 1.0) / (2.0 * e + 1.0); crf = (1.0 / rc) * (3.0 * e) / (2.0 * e + 1.0); }
+                    P_.krf = (T)krf;
+                    P_.crf = (T)crf;
+                }
+            }
+        }
+        P_.geo_sigma = geo_sigma ? 1 : 0;
+        // per-atom LJ parts (zero shortcut folded into a zero eps part)
+        std::vector<T2> ljp(n_);
+        bool uniform = true;
+        for (int64_t i = 0; i < n_; i++) {
+            T s = h_sigma_[i], e = h_eps_[i];
+            bool zero = (!P_.has_lj) || s == (T)0 || e == (T)0;
+            ljp[i].x = zero ? (T)0 : (geo_sigma ? (T)std::sqrt((double)s) : s / (T)2);
+            ljp[i].y = zero ? (T)0 : (T)std::sqrt((double)e);
+            if (h_sigma_[i] != h_sigma_[0] || h_eps_[i] != h_eps_[0]) uniform = false;
+        }
+        if (!P_.has_lj || h_sigma_[0] == (T)0 || h_eps_[0] == (T)0) uniform = uniform && !P_.has_lj;
+        P_.uniform_lj = (uniform && P_.coul_kind == COUL_NONE) ? 1 : 0;
+        if (P_.uniform_lj) {
+            P_.uni_sig2 = P_.has_lj ? h_sigma_[0] * h_sigma_[0] : (T)0;
+            P_.uni_eps = P_.has_lj ? h_eps_[0] : (T)0;
+        }
+        total_mass_ = 0;
+        for (int64_t i = 0; i < n_; i++) total_mass_ += (double)h_mass_[i];
+
+        // per-atom device arrays (original order)
+        const size_t np = (size_t)n_ + 16;
+        MB_CUDA(d_mass_in_.ensure(np * sizeof(T)));
+        MB_CUDA(d_charge_in_.ensure(np * sizeof(T)));
+        MB_CUDA(d_ljp_in_.ensure(np * sizeof(T2)));
+        MB_CUDA(cudaMemcpyAsync(d_mass_in_.p, h_mass_.data(), n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        MB_CUDA(cudaMemcpyAsync(d_charge_in_.p, h_charge_.data(), n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        MB_CUDA(cudaMemcpyAsync(d_ljp_in_.p, ljp.data(), n_ * sizeof(T2), cudaMemcpyHostToDevice, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));  // ljp is a local
+        // slot-order state
+        MB_CUDA(d_pos4_.ensure(np * sizeof(T4)));
+        MB_CUDA(d_vel4_.ensure(np * sizeof(T4)));
+        MB_CUDA(d_f4_.ensure(np * sizeof(T4)));
+        MB_CUDA(d_xref4_.ensure(np * sizeof(T4)));
+        MB_CUDA(d_lj2_.ensure(np * sizeof(T2)));
+        MB_CUDA(d_orig_.ensure(np * sizeof(int)));
+        MB_CUDA(d_inv_orig_.ensure(np * sizeof(int)));
+        MB_CUDA(d_mass_.ensure(np * sizeof(T)));
+        MB_CUDA(cudaMemsetAsync(d_f4_.p, 0, np * sizeof(T4), stream_));
+        MB_CUDA(cudaMemsetAsync(d_lj2_.p, 0, np * sizeof(T2), stream_));
+        MB_CUDA(cudaMemsetAsync(d_pos4_.p, 0, np * sizeof(T4), stream_));
+        MB_CUDA(d_ctl_.ensure(sizeof(Control)));
+        MB_CUDA(cudaMemsetAsync(d_ctl_.p, 0, sizeof(Control), stream_));
+        MB_CUDA(d_cm_.ensure(sizeof(CmState<T>)));
+        MB_CUDA(cudaMemsetAsync(d_cm_.p, 0, sizeof(CmState<T>), stream_));
+        MB_CUDA(d_stage_a_.ensure(3 * np * sizeof(T)));
+        MB_CUDA(d_stage_b_.ensure(3 * np * sizeof(T)));
+        MB_CUDA(d_stage_c_.ensure(3 * np * sizeof(T)));
+        // exclusion CSR
+        auto up = [&](DevBuf& b, const std::vector<int>& v) -> cudaError_t {
+            if (v.empty()) return cudaSuccess;
+            cudaError_t e = b.ensure(v.size() * sizeof(int));
+            if (e != cudaSuccess) return e;
+            return cudaMemcpy(b.p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
+        };
+        MB_CUDA(up(d_ex_ptr_, ex_ptr_)); MB_CUDA(up(d_ex_idx_, ex_idx_));
+        MB_CUDA(up(d_sp_ptr_, sp_ptr_)); MB_CUDA(up(d_sp_idx_, sp_idx_));
+        max_special_host_ = 0;
+        for (size_t i = 0; i + 1 < sp_ptr_.size(); i++) max_special_host_ = std::max(max_special_host_, sp_ptr_[i + 1] - sp_ptr_[i]);
+        const int vvb = (int)((n_ + VV_THREADS - 1) / VV_THREADS);
+        MB_CUDA(d_partial_.ensure((size_t)std::max(vvb, 1024) * 8 * sizeof(double)));
+        have_list_ = false;
+        slots_init_ = false;
+        dirty_ = false;
+        return MB_OK;
+    }
+
+    const int* ex_ptr_dev() const { return ex_ptr_.empty() ? nullptr : d_ex_ptr_.as<int>(); }
+    const int* ex_idx_dev() const { return ex_idx_.empty() ? nullptr : d_ex_idx_.as<int>(); }
+    const int* sp_ptr_dev() const { return sp_ptr_.empty() ? nullptr : d_sp_ptr_.as<int>(); }
+    const int* sp_idx_dev() const { return sp_idx_.empty() ? nullptr : d_sp_idx_.as<int>(); }
+
+    // ------------------------------------------------------------------------------------------
+    // geometry / capacity selection for the brick path
+    int choose_geometry() {
+        Geom<T>& g = g_;
+        memset(&g, 0, sizeof(g));
+        g.n = (int)n_;
+        g.h = 2;
+        g.align = 16 / (int)sizeof(T2);
+        double vol = 1;
+        for (int d = 0; d < 3; d++) {
+            g.L[d] = (T)box_[d];
+            g.invL[d] = (T)(1.0 / box_[d]);
+            g.Ld[d] = box_[d];
+            int nc = (int)std::floor(2.0 * box_[d] / r_list_);
+            nc = std::max(nc, 5);
+            while (nc > 5 && box_[d] / nc < 0.5 * r_list_ * (1.0 + 1e-6)) nc--;
+            g.nc[d] = nc;
+            g.celld[d] = box_[d] / nc;
+            g.inv_cell[d] = (T)(nc / box_[d]);
+            vol *= box_[d];
+        }
+        if ((double)g.nc[0] * g.nc[1] * g.nc[2] > 2.0e8) return set_error(MB_ERR_INVALID, "cell grid too large");
+        g.ncells = g.nc[0] * g.nc[1] * g.nc[2];
+        g.rlist2 = (T)(r_list_ * r_list_);
+        g.skin_half2 = (T)(0.25 * skin_ * skin_);
+        const double rho_c = (double)n_ / g.ncells;
+        const double bytes_per_atom = sizeof(T4) + (P_.uniform_lj ? 0 : sizeof(T2));
+        const double smem_budget = (double)smem_optin_ - 4096;
+        int best[3] = {1, 1, 1};
+        if (user_b_[0] > 0 && user_b_[1] > 0 && user_b_[2] > 0) {
+            for (int d = 0; d < 3; d++) best[d] = std::min(user_b_[d], g.nc[d]);
+        } else {
+            // cost model in pair-evaluation units: every SM works through ceil(nbricks / n_sm) bricks, a brick
+            // costs (owned atoms x neighbours) + ~0.5 per staged halo atom; a lone CTA per SM hides latency badly.
+            const double nbrs = 4.18879 * r_list_ * r_list_ * r_list_ * (double)n_ / vol;
+            double best_t = 1e300;
+            for (int bx = 1; bx <= 8; bx++)
+                for (int by = 1; by <= bx; by++)
+                    for (int bz = 1; bz <= by; bz++) {
+                        if (bx > g.nc[0] || by > g.nc[1] || bz > g.nc[2]) continue;
+                        double halo = (bx + 4.0) * (by + 4.0) * (bz + 4.0) * rho_c * 1.25 + 64;
+                        double smem = halo * bytes_per_atom;
+                        if (smem > smem_budget || halo > 60000) continue;
+                        double occ = std::floor(smem_budget / smem);
+                        double owned = (double)bx * by * bz * rho_c;
+                        double cost_b = owned * nbrs + 0.5 * halo;
+                        double nbr = std::ceil((double)g.nc[0] / bx) * std::ceil((double)g.nc[1] / by) * std::ceil((double)g.nc[2] / bz);
+                        double t = std::ceil(nbr / sm_count_) * cost_b * (occ < 2 ? 1.3 : 1.0);
+                        if (t < best_t * 0.999) { best_t = t; best[0] = bx; best[1] = by; best[2] = bz; }
+                    }
+        }
+        for (int d = 0; d < 3; d++) {
+            g.b[d] = best[d];
+            g.nb[d] = (g.nc[d] + g.b[d] - 1) / g.b[d];
+            g.H[d] = g.b[d] + 2 * g.h;
+        }
+        g.nbricks = g.nb[0] * g.nb[1] * g.nb[2];
+        g.max_runs = 3 * g.H[1] * g.H[2];
+        g.hcells = g.H[0] * g.H[1] * g.H[2];
+        g.n_irows = g.b[1] * g.b[2];
+        return MB_OK;
+    }
+
+    size_t force_smem_bytes() const { return (size_t)g_.halo_cap * (sizeof(T4) + (P_.uniform_lj ? 0 : sizeof(T2))); }
+    size_t build_smem_bytes() const {
+        return (size_t)g_.halo_cap * (sizeof(T4) + sizeof(int)) + (size_t)((g_.hcells + 3) & ~3) * sizeof(ushort2) +
+               (size_t)g_.n_irows * sizeof(IRow);
+    }
+
+    int alloc_brick_tables() {
+        const Geom<T>& g = g_;
+        MB_CUDA(d_cid_.ensure((size_t)(n_ + 16) * sizeof(int)));
+        MB_CUDA(d_perm_.ensure((size_t)(n_ + 16) * sizeof(int)));
+        MB_CUDA(d_cell_count_.ensure((size_t)(g.ncells + 2) * sizeof(int)));
+        MB_CUDA(d_cell_start_.ensure((size_t)(g.ncells + 2) * sizeof(int)));
+        MB_CUDA(d_cell_fill_.ensure((size_t)(g.ncells + 2) * sizeof(int)));
+        MB_CUDA(cudaMemsetAsync(d_cell_count_.p, 0, (size_t)(g.ncells + 2) * sizeof(int), stream_));
+        MB_CUDA(d_hdrs_.ensure((size_t)g.nbricks * sizeof(BrickHdr)));
+        MB_CUDA(d_runs_.ensure((size_t)g.nbricks * g.max_runs * sizeof(Run)));
+        MB_CUDA(d_irows_.ensure((size_t)g.nbricks * g.n_irows * sizeof(IRow)));
+        MB_CUDA(d_hcs_.ensure((size_t)g.nbricks * g.hcells * sizeof(ushort2)));
+        MB_CUDA(d_counts_.ensure((size_t)(n_ + 16) * sizeof(ushort2)));
+        const size_t np = (size_t)n_ + 16;
+        MB_CUDA(d_pos4_t_.ensure(np * sizeof(T4)));
+        MB_CUDA(d_vel4_t_.ensure(np * sizeof(T4)));
+        MB_CUDA(d_lj2_t_.ensure(np * sizeof(T2)));
+        MB_CUDA(d_orig_t_.ensure(np * sizeof(int)));
+        MB_CUDA(d_mass_t_.ensure(np * sizeof(T)));
+        MB_CUDA(d_pe_partial_.ensure((size_t)std::max(g.nbricks, 1) * 7 * sizeof(double)));
+        return MB_OK;
+    }
+
+    // enqueue the gated rebuild sequence. count_only: first pass of the capacity derivation.
+    int enqueue_rebuild(bool lists, bool count_only) {
+        const Geom<T>& g = g_;
+        Control* ctl = d_ctl_.as<Control>();
+        const int nb = (int)((n_ + 255) / 256);
+        prof_.begin(Prof::REBUILD);
+        rebuild_begin_kernel<<<1, 32, 0, stream_>>>(ctl);
+        bin_count_kernel<T><<<nb, 256, 0, stream_>>>(ctl, g, d_pos4_.as<T4>(), d_cid_.as<int>(), d_cell_count_.as<int>());
+        cell_scan_kernel<<<1, 1024, 0, stream_>>>(ctl, g.ncells, g.n, d_cell_count_.as<int>(), d_cell_start_.as<int>(),
+                                                  d_cell_fill_.as<int>());
+        cell_scatter_kernel<<<nb, 256, 0, stream_>>>(ctl, g.n, d_cid_.as<int>(), d_cell_start_.as<int>(),
+                                                     d_cell_fill_.as<int>(), d_perm_.as<int>());
+        cell_sort_kernel<<<(g.ncells + 127) / 128, 128, 0, stream_>>>(ctl, g.ncells, d_cell_start_.as<int>(),
+                                                                     d_perm_.as<int>(), d_cell_count_.as<int>());
+        permute_gather_kernel<T><<<nb, 256, 0, stream_>>>(ctl, g.n, d_perm_.as<int>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
+                                                         d_lj2_.as<T2>(), d_orig_.as<int>(), d_mass_.as<T>(),
+                                                         d_pos4_t_.as<T4>(), d_vel4_t_.as<T4>(), d_lj2_t_.as<T2>(),
+                                                         d_orig_t_.as<int>(), d_mass_t_.as<T>());
+        permute_commit_kernel<T><<<nb, 256, 0, stream_>>>(ctl, g.n, d_pos4_t_.as<T4>(), d_vel4_t_.as<T4>(), d_lj2_t_.as<T2>(),
+                                                         d_orig_t_.as<int>(), d_mass_t_.as<T>(), d_pos4_.as<T4>(),
+                                                         d_vel4_.as<T4>(), d_lj2_.as<T2>(), d_orig_.as<int>(), d_mass_.as<T>(),
+                                                         d_xref4_.as<T4>(), d_inv_orig_.as<int>());
+        brick_tables_kernel<T><<<g.nbricks, 128, 2 * g.max_runs * sizeof(int), stream_>>>(
+            ctl, g, d_cell_start_.as<int>(), d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(),
+            d_hcs_.as<ushort2>(), P_.uniform_lj);
+        launches_ += 8;
+        if (lists) {
+            const size_t smem = build_smem_bytes();
+            if (count_only) {
+                MB_CUDA(cudaFuncSetAttribute(build_lists_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                build_lists_kernel<T, true><<<g.nbricks, 256, smem, stream_>>>(
+                    ctl, g, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(), d_hcs_.as<ushort2>(),
+                    d_pos4_.as<T4>(), d_orig_.as<int>(), ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(), nullptr,
+                    nullptr, nullptr);
+            } else {
+                MB_CUDA(cudaFuncSetAttribute(build_lists_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                build_lists_kernel<T, false><<<g.nbricks, 256, smem, stream_>>>(
+                    ctl, g, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(), d_hcs_.as<ushort2>(),
+                    d_pos4_.as<T4>(), d_orig_.as<int>(), ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(),
+                    d_list_.as<unsigned short>(), d_slist_.as<unsigned short>(), d_counts_.as<ushort2>());
+            }
+            launches_ += 1;
+        }
+        if (!count_only) {
+            rebuild_finish_kernel<<<1, 32, 0, stream_>>>(ctl);
+            launches_ += 1;
+        }
+        prof_.end(Prof::REBUILD);
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
+
+    int read_ctl(Control& c) {
+        MB_CUDA(cudaMemcpyAsync(&c, d_ctl_.p, sizeof(Control), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        return MB_OK;
+    }
+    int set_flag_rebuild() {
+        static const int one = 1;
+        MB_CUDA(cudaMemcpyAsync(&d_ctl_.as<Control>()->rebuild, &one, sizeof(int), cudaMemcpyHostToDevice, stream_));
+        return MB_OK;
+    }
+
+    // Synchronous first build: derives halo capacity and list stride from the actual configuration.
+    // coords_dev: n x 3 device array in original order.
+    int first_build(const T* coords_dev) {
+        const int nb = (int)((n_ + 255) / 256);
+        init_slots_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, coords_dev, d_charge_in_.as<T>(), d_ljp_in_.as<T2>(),
+                                                      d_mass_in_.as<T>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(), d_lj2_.as<T2>(),
+                                                      d_orig_.as<int>(), d_inv_orig_.as<int>(), d_mass_.as<T>(), d_xref4_.as<T4>());
+        launches_++;
+        slots_init_ = true;
+        for (int attempt = 0; attempt < 8; attempt++) {
+            MB_TRY(choose_geometry());
+            MB_TRY(alloc_brick_tables());
+            // pass A: sort + tables with unlimited halo capacity to measure
+            g_.halo_cap = 65535;
+            g_.stride = 0;
+            g_.sstride = 0;
+            MB_TRY(set_flag_rebuild());
+            MB_TRY(enqueue_rebuild(false, true));
+            Control c;
+            MB_TRY(read_ctl(c));
+            int cap = (int)(c.max_halo * (1.0 + 0.15 * cap_scale_)) + 64;
+            cap = (cap + 63) & ~63;
+            g_.halo_cap = std::min(cap, 65535);
+            size_t need = std::max(force_smem_bytes() + 2048, build_smem_bytes() + 1024);
+            if (c.max_halo >= 65000 || need > smem_optin_) {
+                // shrink the brick and retry
+                int* ub = user_b_;
+                int cur[3] = {g_.b[0], g_.b[1], g_.b[2]};
+                int dmax = 0;
+                for (int d = 1; d < 3; d++) if (cur[d] > cur[dmax]) dmax = d;
+                if (cur[dmax] == 1) return set_error(MB_ERR_CAPACITY, "halo of a single cell does not fit in shared memory (density too high for r_list)");
+                cur[dmax]--;
+                for (int d = 0; d < 3; d++) ub[d] = cur[d];
+                continue;
+            }
+            // pass B: count neighbours (flag still set because finish did not run)
+            {
+                const size_t smem = build_smem_bytes();
+                MB_CUDA(cudaFuncSetAttribute(build_lists_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                build_lists_kernel<T, true><<<g_.nbricks, 256, smem, stream_>>>(
+                    d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(), d_hcs_.as<ushort2>(),
+                    d_pos4_.as<T4>(), d_orig_.as<int>(), ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(), nullptr, nullptr,
+                    nullptr);
+                launches_++;
+                MB_CUDA(cudaGetLastError());
+            }
+            MB_TRY(read_ctl(c));
+            int stride = (int)(c.max_neighbors * (1.0 + 0.10 * cap_scale_)) + 16;
+            stride = (stride + 31) & ~31;
+            g_.stride = std::max(stride, 32);
+            g_.sstride = std::max(8, (std::max(c.max_special, max_special_host_) + 7) & ~7);
+            MB_CUDA(d_list_.ensure((size_t)(n_ + 16) * g_.stride * sizeof(unsigned short)));
+            MB_CUDA(d_slist_.ensure((size_t)(n_ + 16) * g_.sstride * sizeof(unsigned short)));
+            // pass C: the real build. The positions are already sorted; the pipeline is idempotent.
+            MB_TRY(enqueue_rebuild(true, false));
+            MB_TRY(read_ctl(c));
+            if (c.overflow) return set_error(MB_ERR_CAPACITY, "neighbour capacity overflow during first build");
+            last_ctl_ = c;
+            have_list_ = true;
+            return MB_OK;
+        }
+        return set_error(MB_ERR_CAPACITY, "could not find a brick size that fits in shared memory");
+    }
+
+    // ------------------------------------------------------------------------------------------
+    template <int COUL, bool UNIFORM, bool SHIFT, bool ENERGY>
+    int launch_force_t(ForceOut<T> out) {
+        const size_t smem = force_smem_bytes();
+        auto launch = [&](auto kern) -> int {
+            MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prof_.begin(Prof::FORCE);
+            kern<<<g_.nbricks, FORCE_THREADS, smem, stream_>>>(g_, P_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
+                                                               d_irows_.as<IRow>(), d_pos4_.as<T4>(), d_lj2_.as<T2>(),
+                                                               d_list_.as<unsigned short>(), d_slist_.as<unsigned short>(),
+                                                               d_counts_.as<ushort2>(), out);
+            prof_.end(Prof::FORCE);
+            return MB_OK;
+        };
+        switch (lpa_) {
+            case 4: MB_TRY(launch(brick_force_kernel<T, COUL, UNIFORM, SHIFT, ENERGY, 4>)); break;
+            case 16: MB_TRY(launch(brick_force_kernel<T, COUL, UNIFORM, SHIFT, ENERGY, 16>)); break;
+            default: MB_TRY(launch(brick_force_kernel<T, COUL, UNIFORM, SHIFT, ENERGY, 8>)); break;
+        }
+        launches_++;
+        n_force_evals_++;
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
+    template <int COUL, bool UNIFORM>
+    int launch_force_c(bool energy, ForceOut<T> out) {
+        if (shift_) return energy ? launch_force_t<COUL, UNIFORM, true, true>(out) : launch_force_t<COUL, UNIFORM, true, false>(out);
+        return energy ? launch_force_t<COUL, UNIFORM, false, true>(out) : launch_force_t<COUL, UNIFORM, false, false>(out);
+    }
+    int launch_force(bool energy) {
+        ForceOut<T> out;
+        out.f4 = d_f4_.as<T4>();
+        out.pe_partial = d_pe_partial_.as<double>();
+        out.vir_partial = d_pe_partial_.as<double>() + g_.nbricks;
+        switch (P_.coul_kind) {
+            case COUL_NONE:
+                return P_.uniform_lj ? launch_force_c<COUL_NONE, true>(energy, out) : launch_force_c<COUL_NONE, false>(energy, out);
+            case COUL_PLAIN: return launch_force_c<COUL_PLAIN, false>(energy, out);
+            case COUL_CRF: return launch_force_c<COUL_CRF, false>(energy, out);
+            default: return launch_force_c<COUL_EWALD, false>(energy, out);
+        }
+    }
+
+    template <int COUL>
+    int launch_allpairs_c(bool energy, const T4* posq, const T2* lj2, T4* f4, int nblk) {
+        double* pe = d_pe_partial_.as<double>();
+        double* vir = pe + nblk;
+        T Lx = (T)box_[0], Ly = (T)box_[1], Lz = (T)box_[2];
+#define MB_AP(SH, EN)                                                                                              \
+    allpairs_force_kernel<T, COUL, SH, EN><<<nblk, AP_THREADS, 0, stream_>>>((int)n_, P_, Lx, Ly, Lz, posq, lj2,    \
+                                                                              ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), \
+                                                                              sp_idx_dev(), f4, pe, vir)
+        prof_.begin(Prof::FORCE);
+        if (shift_) { if (energy) MB_AP(true, true); else MB_AP(true, false); }
+        else { if (energy) MB_AP(false, true); else MB_AP(false, false); }
+        prof_.end(Prof::FORCE);
+#undef MB_AP
+        launches_++;
+        n_force_evals_++;
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
+    int launch_allpairs(bool energy, const T4* posq, const T2* lj2, T4* f4) {
+        const int nblk = (int)((n_ + AP_THREADS - 1) / AP_THREADS);
+        MB_CUDA(d_pe_partial_.ensure((size_t)nblk * 7 * sizeof(double)));
+        switch (P_.coul_kind) {
+            case COUL_NONE: return launch_allpairs_c<COUL_NONE>(energy, posq, lj2, f4, nblk);
+            case COUL_PLAIN: return launch_allpairs_c<COUL_PLAIN>(energy, posq, lj2, f4, nblk);
+            case COUL_CRF: return launch_allpairs_c<COUL_CRF>(energy, posq, lj2, f4, nblk);
+            default: return launch_allpairs_c<COUL_EWALD>(energy, posq, lj2, f4, nblk);
+        }
+    }
+
+    // host/device argument views ----------------------------------------------------------------
+    // returns a device pointer holding `count` T values of `user` (copying if user is a host pointer)
+    int view_in(const void* user, size_t count, DevBuf& stage, const T** out) {
+        if (!user) { *out = nullptr; return MB_OK; }
+        if (is_device_ptr(user)) { *out = reinterpret_cast<const T*>(user); return MB_OK; }
+        MB_CUDA(stage.ensure(count * sizeof(T)));
+        MB_CUDA(cudaMemcpyAsync(stage.p, user, count * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        *out = stage.as<T>();
+        return MB_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // make the slot-order state reflect `coords` (and vels), rebuilding the list when required
+    int sync_state_from(const T* coords_dev, const T* vels_dev) {
+        const int nb = (int)((n_ + 255) / 256);
+        if (!have_list_) {
+            MB_TRY(first_build(coords_dev));
+            if (vels_dev) {
+                ingest_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_, coords_dev, vels_dev, d_orig_.as<int>(), d_xref4_.as<T4>(),
+                                                          d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->disp);
+                launches_++;
+            }
+            return MB_OK;
+        }
+        ingest_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_, coords_dev, vels_dev, d_orig_.as<int>(), d_xref4_.as<T4>(),
+                                                  d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->rebuild);
+        launches_++;
+        MB_TRY(enqueue_rebuild(true, false));
+        return MB_OK;
+    }
+
+    int check_overflow_sync() {
+        Control c;
+        MB_TRY(read_ctl(c));
+        last_ctl_ = c;
+        if (c.overflow) {
+            have_list_ = false;  // next call re-derives capacities
+            static const int zero = 0;
+            cudaMemcpyAsync(&d_ctl_.as<Control>()->overflow, &zero, sizeof(int), cudaMemcpyHostToDevice, stream_);
+            return set_error(MB_ERR_CAPACITY, "neighbour/halo capacity overflow; results of this call are invalid, retry");
+        }
+        return MB_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    int forces_energy(const void* coords, void* fs, void* pe, void* vir, int64_t step_n) override {
+        (void)step_n;
+        MB_TRY(prepare());
+        if (!coords) return set_error(MB_ERR_INVALID, "coords is null");
+        const T* xc = nullptr;
+        MB_TRY(view_in(coords, 3 * (size_t)n_, d_stage_a_, &xc));
+        const bool energy = (pe != nullptr) || (vir != nullptr);
+        const int nb = (int)((n_ + 255) / 256);
+        int n_partials = 0;
+        const int* orig = nullptr;
+        if (path_ == 0) {
+            // original order; posq packed into pos4
+            init_slots_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, xc, d_charge_in_.as<T>(), d_ljp_in_.as<T2>(), d_mass_in_.as<T>(),
+                                                          d_pos4_.as<T4>(), d_vel4_.as<T4>(), d_lj2_.as<T2>(), d_orig_.as<int>(),
+                                                          d_inv_orig_.as<int>(), d_mass_.as<T>(), d_xref4_.as<T4>());
+            launches_++;
+            MB_TRY(launch_allpairs(energy, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
+            n_partials = (int)((n_ + AP_THREADS - 1) / AP_THREADS);
+        } else {
+            MB_TRY(sync_state_from(xc, nullptr));
+            MB_TRY(launch_force(energy));
+            n_partials = g_.nbricks;
+            orig = d_orig_.as<int>();
+        }
+        // outputs (ADD semantics)
+        if (fs) {
+            if (is_device_ptr(fs)) {
+                scatter_forces_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, d_f4_.as<T4>(), orig, reinterpret_cast<T*>(fs));
+                launches_++;
+            } else {
+                MB_CUDA(d_stage_b_.ensure(3 * (size_t)n_ * sizeof(T)));
+                MB_CUDA(cudaMemcpyAsync(d_stage_b_.p, fs, 3 * (size_t)n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+                scatter_forces_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, d_f4_.as<T4>(), orig, d_stage_b_.as<T>());
+                launches_++;
+                MB_CUDA(cudaMemcpyAsync(fs, d_stage_b_.p, 3 * (size_t)n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+            }
+        }
+        if (energy) {
+            // stage scalars on device: [pe, vir(9)]
+            MB_CUDA(d_scalars_.ensure(16 * sizeof(T)));
+            T host_sc[16] = {0};
+            bool pe_dev = pe && is_device_ptr(pe), vir_dev = vir && is_device_ptr(vir);
+            T* pe_target = nullptr;
+            T* vir_target = nullptr;
+            if (pe) {
+                if (pe_dev) pe_target = reinterpret_cast<T*>(pe);
+                else { host_sc[0] = *reinterpret_cast<T*>(pe); pe_target = d_scalars_.as<T>(); }
+            }
+            if (vir) {
+                if (vir_dev) vir_target = reinterpret_cast<T*>(vir);
+                else { memcpy(host_sc + 1, vir, 9 * sizeof(T)); vir_target = d_scalars_.as<T>() + 1; }
+            }
+            if ((pe && !pe_dev) || (vir && !vir_dev))
+                MB_CUDA(cudaMemcpyAsync(d_scalars_.p, host_sc, 16 * sizeof(T), cudaMemcpyHostToDevice, stream_));
+            double* pp = d_pe_partial_.as<double>();
+            reduce_partials_kernel<T><<<1, 256, 0, stream_>>>(n_partials, pp, pp + n_partials, pe_target, vir_target, nullptr);
+            launches_++;
+            if ((pe && !pe_dev) || (vir && !vir_dev)) {
+                MB_CUDA(cudaMemcpyAsync(host_sc, d_scalars_.p, 16 * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+                MB_CUDA(cudaStreamSynchronize(stream_));
+                if (pe && !pe_dev) *reinterpret_cast<T*>(pe) = host_sc[0];
+                if (vir && !vir_dev) memcpy(vir, host_sc + 1, 9 * sizeof(T));
+            }
+        }
+        MB_CUDA(cudaGetLastError());
+        if (path_ == 1) MB_TRY(check_overflow_sync());
+        else MB_CUDA(cudaStreamSynchronize(stream_));
+        return MB_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    int simulate_vv(void* coords, void* vels, const mb_vv_params_t* p) override {
+        MB_TRY(prepare());
+        if (!coords || !vels || !p) return set_error(MB_ERR_INVALID, "null argument");
+        if (p->n_steps < 0 || !(p->dt > 0)) return set_error(MB_ERR_INVALID, "n_steps < 0 or dt <= 0");
+        const bool c_dev = is_device_ptr(coords), v_dev = is_device_ptr(vels);
+        const T* xc = nullptr;
+        const T* vc = nullptr;
+        MB_TRY(view_in(coords, 3 * (size_t)n_, d_stage_a_, &xc));
+        MB_TRY(view_in(vels, 3 * (size_t)n_, d_stage_c_, &vc));
+        const int nb = (int)((n_ + 255) / 256);
+        const int vvb = (int)((n_ + VV_THREADS - 1) / VV_THREADS);
+        Control* ctl = d_ctl_.as<Control>();
+        CmState<T>* cm = d_cm_.as<CmState<T>>();
+        const T dt = (T)p->dt, dt_half = (T)p->dt / (T)2;
+        const double inv_mass = (total_mass_ > 0) ? 1.0 / total_mass_ : 0.0;
+        clear_cm_kernel<T><<<1, 1, 0, stream_>>>(cm);
+        launches_++;
+        const bool thermostat = p->andersen_kT > 0 && p->andersen_prob > 0;
+        T skin_half2 = g_.skin_half2;
+        int* flag_ptr = nullptr;
+        if (path_ == 0) {
+            init_slots_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, xc, d_charge_in_.as<T>(), d_ljp_in_.as<T2>(), d_mass_in_.as<T>(),
+                                                          d_pos4_.as<T4>(), d_vel4_.as<T4>(), d_lj2_.as<T2>(), d_orig_.as<int>(),
+                                                          d_inv_orig_.as<int>(), d_mass_.as<T>(), d_xref4_.as<T4>());
+            launches_++;
+            // velocities + wrap through ingest with an identity order (geometry only needs L)
+            Geom<T> g0;
+            memset(&g0, 0, sizeof(g0));
+            for (int d = 0; d < 3; d++) { g0.L[d] = (T)box_[d]; g0.invL[d] = (T)(1.0 / box_[d]); }
+            g0.skin_half2 = std::numeric_limits<T>::infinity();
+            g_ap_ = g0;
+            ingest_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g0, xc, vc, d_orig_.as<int>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(),
+                                                      d_vel4_.as<T4>(), &ctl->disp);
+            wrap_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g0, d_pos4_.as<T4>());
+            launches_ += 2;
+            skin_half2 = std::numeric_limits<T>::infinity();
+            flag_ptr = &ctl->disp;
+        } else {
+            MB_TRY(sync_state_from(xc, vc));
+            flag_ptr = (rebuild_every_ == 0) ? &ctl->rebuild : &ctl->disp;
+        }
+        auto force_eval = [&]() -> int {
+            if (path_ == 0) return launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>());
+            return launch_force(false);
+        };
+        bool cm_pending = false;  // host mirror of cm->valid
+        if (p->init_step == 0 && p->remove_cm_every != 0) {
+            // remove_CM_motion! before the first force evaluation (simulators.jl:563): zero-length kick
+            vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>((int)n_, (T)0, 1, inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
+                                                                d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0);
+            launches_++;
+            cm_pending = true;
+        }
+        MB_TRY(force_eval());
+        for (int64_t k = 1; k <= p->n_steps; k++) {
+            const int64_t step_n = p->init_step + k;
+            prof_.begin(Prof::VV);
+            vv_kick_drift_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, dt, dt_half, skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(),
+                                                             d_pos4_.as<T4>(), d_vel4_.as<T4>(), flag_ptr);
+            prof_.end(Prof::VV);
+            launches_++;
+            const int do_cm = (p->remove_cm_every != 0 && step_n % p->remove_cm_every == 0) ? 1 : 0;
+            if (cm_pending && !do_cm) {  // K1 consumed v_cm; nothing will overwrite it this step
+                clear_cm_kernel<T><<<1, 1, 0, stream_>>>(cm);
+                launches_++;
+            }
+            cm_pending = false;
+            if (path_ == 0) {
+                wrap_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_ap_, d_pos4_.as<T4>());
+                launches_++;
+            } else {
+                if (rebuild_every_ > 0 && k > 1 && (step_n - 1) % rebuild_every_ == 0) MB_TRY(set_flag_rebuild());
+                if (rebuild_every_ == 0 || (k > 1 && (step_n - 1) % rebuild_every_ == 0)) MB_TRY(enqueue_rebuild(true, false));
+            }
+            MB_TRY(force_eval());
+            prof_.begin(Prof::VV);
+            vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>((int)n_, dt_half, do_cm, inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
+                                                                d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0);
+            prof_.end(Prof::VV);
+            launches_++;
+            cm_pending = do_cm != 0;
+            if (thermostat) {
+                andersen_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, (T)p->andersen_kT, p->andersen_prob, (uint32_t)p->rng_ctr1,
+                                                            (uint32_t)(p->rng_ctr1 >> 32), (uint32_t)p->rng_key,
+                                                            (uint32_t)(p->rng_key >> 32), (uint32_t)step_n, d_orig_.as<int>(),
+                                                            d_mass_.as<T>(), d_vel4_.as<T4>(), cm, ctl);
+                launches_++;
+                cm_pending = false;
+            }
+            n_steps_++;
+        }
+        // export
+        T* xo = c_dev ? reinterpret_cast<T*>(coords) : d_stage_a_.as<T>();
+        T* vo = v_dev ? reinterpret_cast<T*>(vels) : d_stage_c_.as<T>();
+        export_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, path_ == 0 ? g_ap_ : g_, d_pos4_.as<T4>(), d_vel4_.as<T4>(), d_orig_.as<int>(), cm,
+                                                  xo, vo);
+        launches_++;
+        if (!c_dev) MB_CUDA(cudaMemcpyAsync(coords, xo, 3 * (size_t)n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+        if (!v_dev) MB_CUDA(cudaMemcpyAsync(vels, vo, 3 * (size_t)n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaGetLastError());
+        if (path_ == 1) MB_TRY(check_overflow_sync());
+        else MB_CUDA(cudaStreamSynchronize(stream_));
+        return MB_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    int remove_cm(void* vels) override {
+        MB_TRY(prepare());
+        if (!vels) return set_error(MB_ERR_INVALID, "null velocities");
+        const bool dev = is_device_ptr(vels);
+        const T* vc = nullptr;
+        MB_TRY(view_in(vels, 3 * (size_t)n_, d_stage_c_, &vc));
+        const int nb = (int)((n_ + 255) / 256);
+        MB_CUDA(d_partial_.ensure((size_t)nb * 3 * sizeof(double)));
+        momentum_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, vc, d_mass_in_.as<T>(), d_partial_.as<double>());
+        launches_++;
+        std::vector<double> part((size_t)nb * 3);
+        MB_CUDA(cudaMemcpyAsync(part.data(), d_partial_.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        double s[3] = {0, 0, 0};
+        for (int b = 0; b < nb; b++) for (int d = 0; d < 3; d++) s[d] += part[3 * (size_t)b + d];
+        T* vw = const_cast<T*>(vc);
+        subtract_velocity_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, (T)(s[0] / total_mass_), (T)(s[1] / total_mass_),
+                                                             (T)(s[2] / total_mass_), vw);
+        launches_++;
+        if (!dev) MB_CUDA(cudaMemcpyAsync(vels, vw, 3 * (size_t)n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        return MB_OK;
+    }
+    int kinetic_energy(const void* vels, double* out) override {
+        MB_TRY(prepare());
+        if (!vels || !out) return set_error(MB_ERR_INVALID, "null argument");
+        const T* vc = nullptr;
+        MB_TRY(view_in(vels, 3 * (size_t)n_, d_stage_c_, &vc));
+        const int nb = (int)((n_ + 255) / 256);
+        MB_CUDA(d_partial_.ensure((size_t)nb * 3 * sizeof(double)));
+        kinetic_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, vc, d_mass_in_.as<T>(), d_partial_.as<double>());
+        launches_++;
+        std::vector<double> part(nb);
+        MB_CUDA(cudaMemcpyAsync(part.data(), d_partial_.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        double s = 0;
+        for (double v : part) s += v;
+        *out = s;
+        return MB_OK;
+    }
+    int rebuild(const void* coords) override {
+        MB_TRY(prepare());
+        if (path_ == 0) return MB_OK;
+        const T* xc = nullptr;
+        MB_TRY(view_in(coords, 3 * (size_t)n_, d_stage_a_, &xc));
+        have_list_ = false;
+        MB_TRY(sync_state_from(xc, nullptr));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        return MB_OK;
+    }
+    int stats(mb_stats_t* o) override {
+        memset(o, 0, sizeof(*o));
+        o->n_atoms = n_;
+        o->n_force_evals = n_force_evals_;
+        o->n_steps = n_steps_;
+        o->path = path_;
+        o->r_list = r_list_;
+        o->kernel_launches = launches_;
+        prof_.collect();
+        o->force_ms = prof_.ms[Prof::FORCE]; o->force_launches = prof_.count[Prof::FORCE];
+        o->vv_ms = prof_.ms[Prof::VV]; o->vv_launches = prof_.count[Prof::VV];
+        o->rebuild_ms = prof_.ms[Prof::REBUILD]; o->rebuild_launches = prof_.count[Prof::REBUILD];
+        if (d_ctl_.p && !dirty_) {
+            Control c;
+            MB_TRY(read_ctl(c));
+            o->n_rebuilds = (int64_t)c.n_rebuilds;
+            o->n_pairs_in_list = (int64_t)c.n_pairs;
+            o->max_neighbors = c.max_neighbors;
+            o->max_halo = c.max_halo;
+            o->violations = c.violations;
+        }
+        if (path_ == 1 && have_list_) {
+            o->n_list_entries = (int64_t)n_ * g_.stride;
+            o->n_bricks = g_.nbricks;
+            for (int d = 0; d < 3; d++) { o->n_cells[d] = g_.nc[d]; o->brick_dims[d] = g_.b[d]; }
+            o->halo_capacity = g_.halo_cap;
+            o->list_stride = g_.stride;
+        }
+        return MB_OK;
+    }
+
+   private:
+    int device_;
+    cudaStream_t stream_;
+    int sm_count_ = 148;
+    size_t smem_optin_ = 232448;
+    int64_t n_ = 0;
+    std::vector<T> h_mass_, h_charge_, h_sigma_, h_eps_;
+    double box_[3];
+    std::vector<mb_inter_t> inters_;
+    std::vector<int> ex_ptr_, ex_idx_, sp_ptr_, sp_idx_;
+    int max_special_host_ = 0;
+    double r_list_ = 0, skin_ = 0, cap_scale_ = 1.0, total_mass_ = 0;
+    int rebuild_every_ = 0;
+    int user_b_[3] = {0, 0, 0};
+    int lpa_ = 8;
+    bool dirty_ = true, have_list_ = false, slots_init_ = false, shift_ = false;
+    int path_ = 0;
+    PairParams<T> P_;
+    Geom<T> g_, g_ap_;
+    Control last_ctl_;
+    int64_t launches_ = 0, n_force_evals_ = 0, n_steps_ = 0;
+    Prof prof_;
+    DevBuf d_mass_in_, d_charge_in_, d_ljp_in_;
+    DevBuf d_pos4_, d_vel4_, d_f4_, d_xref4_, d_lj2_, d_orig_, d_inv_orig_, d_mass_;
+    DevBuf d_pos4_t_, d_vel4_t_, d_lj2_t_, d_orig_t_, d_mass_t_;
+    DevBuf d_ctl_, d_cm_, d_stage_a_, d_stage_b_, d_stage_c_, d_scalars_;
+    DevBuf d_ex_ptr_, d_ex_idx_, d_sp_ptr_, d_sp_idx_;
+    DevBuf d_cid_, d_perm_, d_cell_count_, d_cell_start_, d_cell_fill_;
+    DevBuf d_hdrs_, d_runs_, d_irows_, d_hcs_, d_counts_, d_list_, d_slist_;
+    DevBuf d_partial_, d_pe_partial_;
+};
+
+}  // namespace mb
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+struct mb_ctx {
+    std::unique_ptr<mb::EngineBase> e;
+    int device;
+    int dtype;
+};
+
+#define MB_CTX_GUARD(ctx)                                                         \
+    if (!(ctx) || !(ctx)->e) return mb::set_error(MB_ERR_INVALID, "null context"); \
+    if (cudaSetDevice((ctx)->device) != cudaSuccess) return mb::set_error(MB_ERR_CUDA, "cudaSetDevice failed")
+
+extern "C" {
+
+const char* mb_last_error(void) { return mb::g_last_error.c_str(); }
+
+int mb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mb_ctx_create(int device, int dtype, void* cuda_stream, mb_ctx** out) {
+    if (!out) return mb::set_error(MB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (dtype != 32 && dtype != 64) return mb::set_error(MB_ERR_INVALID, "dtype must be 32 or 64");
+    int n = mb_device_count();
+    if (n <= 0) return mb::set_error(MB_ERR_NOGPU, "no CUDA device visible: libmollyb200 has no CPU fallback");
+    if (device < 0 || device >= n) return mb::set_error(MB_ERR_INVALID, "device index out of range");
+    if (cudaSetDevice(device) != cudaSuccess) return mb::set_error(MB_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return mb::set_error(MB_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major < 10)
+        return mb::set_error(MB_ERR_NOGPU, std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
+    mb_ctx* c = new mb_ctx();
+    c->device = device;
+    c->dtype = dtype;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (dtype == 32) c->e.reset(new mb::Engine<float>(device, s));
+    else c->e.reset(new mb::Engine<double>(device, s));
+    *out = c;
+    return MB_OK;
+}
+void mb_ctx_destroy(mb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    delete ctx;
+}
+int mb_set_atoms(mb_ctx* ctx, int64_t n, const void* atoms_aos) { MB_CTX_GUARD(ctx); return ctx->e->set_atoms_aos(n, atoms_aos); }
+int mb_set_atoms_soa(mb_ctx* ctx, int64_t n, const void* mass, const void* charge, const void* sigma, const void* eps) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->set_atoms_soa(n, mass, charge, sigma, eps);
+}
+int mb_set_box(mb_ctx* ctx, const double side[3]) { MB_CTX_GUARD(ctx); return ctx->e->set_box(side); }
+int mb_set_inters(mb_ctx* ctx, int n_inters, const mb_inter_t* inters) { MB_CTX_GUARD(ctx); return ctx->e->set_inters(n_inters, inters); }
+int mb_set_exceptions(mb_ctx* ctx, int64_t n_excl, const int32_t* ei, const int32_t* ej, int64_t n_spec, const int32_t* si,
+                      const int32_t* sj) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->set_exceptions(n_excl, ei, ej, n_spec, si, sj);
+}
+int mb_set_neighbor_policy(mb_ctx* ctx, double r_list, int rebuild_every) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->set_neighbor_policy(r_list, rebuild_every);
+}
+int mb_forces(mb_ctx* ctx, const void* coords, void* fs_mat, void* virial, int64_t step_n) {
+    MB_CTX_GUARD(ctx);
+    if (!fs_mat) return mb::set_error(MB_ERR_INVALID, "fs_mat is null");
+    return ctx->e->forces_energy(coords, fs_mat, nullptr, virial, step_n);
+}
+int mb_energy(mb_ctx* ctx, const void* coords, void* pe, int64_t step_n) {
+    MB_CTX_GUARD(ctx);
+    if (!pe) return mb::set_error(MB_ERR_INVALID, "pe is null");
+    return ctx->e->forces_energy(coords, nullptr, pe, nullptr, step_n);
+}
+int mb_forces_energy(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, void* virial, int64_t step_n) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->forces_energy(coords, fs_mat, pe, virial, step_n);
+}
+int mb_simulate_vv(mb_ctx* ctx, void* coords, void* vels, const mb_vv_params_t* p) { MB_CTX_GUARD(ctx); return ctx->e->simulate_vv(coords, vels, p); }
+int mb_remove_cm_motion(mb_ctx* ctx, void* vels) { MB_CTX_GUARD(ctx); return ctx->e->remove_cm(vels); }
+int mb_kinetic_energy(mb_ctx* ctx, const void* vels, double* ke_host) { MB_CTX_GUARD(ctx); return ctx->e->kinetic_energy(vels, ke_host); }
+int mb_rebuild_neighbors(mb_ctx* ctx, const void* coords) { MB_CTX_GUARD(ctx); return ctx->e->rebuild(coords); }
+int mb_stats(mb_ctx* ctx, mb_stats_t* host_out) {
+    MB_CTX_GUARD(ctx);
+    if (!host_out) return mb::set_error(MB_ERR_INVALID, "null stats");
+    return ctx->e->stats(host_out);
+}
+int mb_synchronize(mb_ctx* ctx) { MB_CTX_GUARD(ctx); return ctx->e->synchronize(); }
+int mb_set_capacity_scale(mb_ctx* ctx, double scale) { MB_CTX_GUARD(ctx); return ctx->e->set_capacity_scale(scale); }
+int mb_set_launch_config(mb_ctx* ctx, const int32_t brick_dims[3], int32_t lanes_per_atom) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->set_launch_config(brick_dims, lanes_per_atom);
+}
+int mb_set_profiling(mb_ctx* ctx, int enable) { MB_CTX_GUARD(ctx); return ctx->e->set_profiling(enable); }
+int mb_set_decomposition(mb_ctx* ctx, const mb_decomp_t* d) {
+    MB_CTX_GUARD(ctx);
+    (void)d;
+    return mb::set_error(MB_ERR_INVALID, "spatial decomposition is driven by the host runtime (see DESIGN.md); not available in this build");
+}
+
+}  // extern "C"

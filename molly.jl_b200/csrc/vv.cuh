@@ -1,0 +1,327 @@
+// vv.cuh — fused VelocityVerlet kernels and the original-order <-> slot-order movers.
+//
+// Reference: simulate!(sys, ::VelocityVerlet, n) src/simulators.jl:547-668 runs the update as five
+// separate broadcasts + two CM-removal kernels per step; here it is
+//   K1  v -= v_cm (pending);  v += (F/m) dt/2;  x += v dt;  displacement check     (one pass)
+//   F   brick_force_kernel
+//   K2  v += (F/m) dt/2;  sum(m v) -> v_cm (last CTA, fixed order)                  (one pass)
+// Positions stay continuous (unwrapped) between neighbour rebuilds; wrap_coords (src/spatial.jl:573-586)
+// is applied at every rebuild and on export, which is equivalent under the minimum-image convention.
+#pragma once
+#include "cells.cuh"
+
+namespace mb {
+
+template <typename T>
+struct CmState {
+    T v[3];
+    int valid;
+};
+
+// ---- first-touch initialisation: slot order = original order -------------------------------------
+template <typename T>
+__global__ void init_slots_kernel(int n, const T* __restrict__ coords, const T* __restrict__ charge,
+                                  const typename VT<T>::T2* __restrict__ ljp, const T* __restrict__ mass_in,
+                                  typename VT<T>::T4* __restrict__ pos4, typename VT<T>::T4* __restrict__ vel4,
+                                  typename VT<T>::T2* __restrict__ lj2, int* __restrict__ orig, int* __restrict__ inv_orig,
+                                  T* __restrict__ mass, typename VT<T>::T4* __restrict__ xref4) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    typename VT<T>::T4 p = make4<T>(coords[3 * s], coords[3 * s + 1], coords[3 * s + 2], charge[s]);
+    pos4[s] = p;
+    xref4[s] = p;
+    T m = mass_in[s];
+    vel4[s] = make4<T>((T)0, (T)0, (T)0, (m == (T)0) ? (T)0 : (T)1 / m);  // calc_accels: massless -> 0
+    lj2[s] = ljp[s];
+    orig[s] = s;
+    inv_orig[s] = s;
+    mass[s] = m;
+}
+
+// ---- ingest coordinates (and velocities) from original order into the current slot order ------
+// The caller's coordinates may have been wrapped by Molly since the last call, so the displacement
+// from the reference position is taken modulo the box and the slot position continued from xref.
+template <typename T>
+__global__ void ingest_kernel(int n, Geom<T> g, const T* __restrict__ coords, const T* __restrict__ vels,
+                              const int* __restrict__ orig, const typename VT<T>::T4* __restrict__ xref4,
+                              typename VT<T>::T4* __restrict__ pos4, typename VT<T>::T4* __restrict__ vel4,
+                              int* __restrict__ flag) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int o = orig[s];
+    typename VT<T>::T4 ref = xref4[s];
+    typename VT<T>::T4 p = pos4[s];
+    T x[3] = {coords[3 * (size_t)o], coords[3 * (size_t)o + 1], coords[3 * (size_t)o + 2]};
+    T r[3] = {ref.x, ref.y, ref.z};
+    T d2 = (T)0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        T dd = x[d] - r[d];
+        dd -= g.L[d] * frint(dd * g.invL[d]);
+        d2 += dd * dd;
+        // keep the caller's value when it is the same image (exact), otherwise continue from xref
+        T cont = r[d] + dd;
+        x[d] = (fabs((double)(x[d] - cont)) < 0.25 * (double)g.L[d]) ? x[d] : cont;
+    }
+    p.x = x[0]; p.y = x[1]; p.z = x[2];
+    pos4[s] = p;
+    if (vels) {
+        typename VT<T>::T4 v = vel4[s];
+        v.x = vels[3 * (size_t)o]; v.y = vels[3 * (size_t)o + 1]; v.z = vels[3 * (size_t)o + 2];
+        vel4[s] = v;
+    }
+    if (d2 > g.skin_half2) *flag = 1;
+}
+
+// ---- export: slot order -> original order, wrapped coordinates, pending CM velocity applied ----
+template <typename T>
+__global__ void export_kernel(int n, Geom<T> g, const typename VT<T>::T4* __restrict__ pos4,
+                              const typename VT<T>::T4* __restrict__ vel4, const int* __restrict__ orig,
+                              const CmState<T>* __restrict__ cm, T* __restrict__ coords, T* __restrict__ vels) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int o = orig[s];
+    if (coords) {
+        typename VT<T>::T4 p = pos4[s];
+        T x[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            T v = x[d] - ffloor(x[d] * g.invL[d]) * g.L[d];
+            if (v >= g.L[d]) v -= g.L[d];
+            if (v < (T)0) v = (T)0;
+            coords[3 * (size_t)o + d] = v;
+        }
+    }
+    if (vels) {
+        typename VT<T>::T4 v = vel4[s];
+        if (cm && cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
+        vels[3 * (size_t)o] = v.x;
+        vels[3 * (size_t)o + 1] = v.y;
+        vels[3 * (size_t)o + 2] = v.z;
+    }
+}
+
+// wrap positions into [0, L) (all-pairs path: the minimum-image select chain needs wrapped coordinates)
+template <typename T>
+__global__ void wrap_kernel(int n, Geom<T> g, typename VT<T>::T4* __restrict__ pos4) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    typename VT<T>::T4 p = pos4[s];
+    T x[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int d = 0; d < 3; d++) x[d] = x[d] - ffloor(x[d] / g.L[d]) * g.L[d];  // wrap_coord_1D
+    p.x = x[0]; p.y = x[1]; p.z = x[2];
+    pos4[s] = p;
+}
+
+// forces: slot order -> ADD into fs_mat (original order, 3 x n column-major)
+template <typename T>
+__global__ void scatter_forces_kernel(int n, const typename VT<T>::T4* __restrict__ f4, const int* __restrict__ orig,
+                                      T* __restrict__ fs_mat) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int o = orig ? orig[s] : s;
+    typename VT<T>::T4 f = f4[s];
+    fs_mat[3 * (size_t)o] += f.x;
+    fs_mat[3 * (size_t)o + 1] += f.y;
+    fs_mat[3 * (size_t)o + 2] += f.z;
+}
+
+// ---- K1: first half kick + drift + displacement check ------------------------------------------
+template <typename T>
+__global__ void vv_kick_drift_kernel(int n, T dt, T dt_half, T skin_half2, const CmState<T>* __restrict__ cm,
+                                     const typename VT<T>::T4* __restrict__ f4,
+                                     const typename VT<T>::T4* __restrict__ xref4, typename VT<T>::T4* __restrict__ pos4,
+                                     typename VT<T>::T4* __restrict__ vel4, int* __restrict__ flag) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    typename VT<T>::T4 v = vel4[s];
+    const typename VT<T>::T4 f = f4[s];
+    typename VT<T>::T4 p = pos4[s];
+    const typename VT<T>::T4 r = xref4[s];
+    if (cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
+    const T a = v.w * dt_half;  // (1/m) dt/2
+    v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
+    p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
+    vel4[s] = v;
+    pos4[s] = p;
+    const T dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
+    if (dx * dx + dy * dy + dz * dz > skin_half2) *flag = 1;
+}
+
+// ---- K2: second half kick + centre-of-mass momentum -------------------------------------------
+// Every CTA writes its partial sum(m v); the last CTA to finish adds the partials in index order
+// (deterministic) and publishes v_cm = sum(m v) / sum(m) (src/spatial.jl:901-916). The subtraction is
+// applied lazily by the next reader of the velocities (K1, the thermostat or export).
+constexpr int VV_THREADS = 256;
+template <typename T>
+__global__ void __launch_bounds__(VV_THREADS)
+    vv_kick2_kernel(int n, T dt_half, int do_cm, double inv_total_mass, const typename VT<T>::T4* __restrict__ f4,
+                    const T* __restrict__ mass, typename VT<T>::T4* __restrict__ vel4, double* __restrict__ partial,
+                    Control* __restrict__ ctl, CmState<T>* __restrict__ cm, int apply_pending) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    double px = 0, py = 0, pz = 0;
+    if (s < n) {
+        typename VT<T>::T4 v = vel4[s];
+        if (apply_pending && cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
+        const typename VT<T>::T4 f = f4[s];
+        const T a = v.w * dt_half;
+        v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
+        vel4[s] = v;
+        const T m = mass[s];
+        px = (double)(v.x * m); py = (double)(v.y * m); pz = (double)(v.z * m);
+    }
+    if (!do_cm) return;
+    __shared__ double s_red[VV_THREADS / 32][3];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        px += __shfl_xor_sync(0xffffffffu, px, o);
+        py += __shfl_xor_sync(0xffffffffu, py, o);
+        pz += __shfl_xor_sync(0xffffffffu, pz, o);
+    }
+    if (lane == 0) { s_red[wid][0] = px; s_red[wid][1] = py; s_red[wid][2] = pz; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < VV_THREADS / 32; w++) { a += s_red[w][0]; b += s_red[w][1]; c += s_red[w][2]; }
+        partial[3 * (size_t)blockIdx.x] = a;
+        partial[3 * (size_t)blockIdx.x + 1] = b;
+        partial[3 * (size_t)blockIdx.x + 2] = c;
+        __threadfence();
+        unsigned int t = atomicInc(&ctl->ticket, gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double a = 0, b = 0, c = 0;
+        for (int i = tid; i < (int)gridDim.x; i += VV_THREADS) {
+            a += partial[3 * (size_t)i]; b += partial[3 * (size_t)i + 1]; c += partial[3 * (size_t)i + 2];
+        }
+        // fixed-shape tree -> deterministic
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        __syncthreads();
+        if (lane == 0) { s_red[wid][0] = a; s_red[wid][1] = b; s_red[wid][2] = c; }
+        __syncthreads();
+        if (tid == 0) {
+            a = b = c = 0;
+            for (int w = 0; w < VV_THREADS / 32; w++) { a += s_red[w][0]; b += s_red[w][1]; c += s_red[w][2]; }
+            cm->v[0] = (T)(a * inv_total_mass);
+            cm->v[1] = (T)(b * inv_total_mass);
+            cm->v[2] = (T)(c * inv_total_mass);
+            cm->valid = 1;
+        }
+    }
+}
+
+// stand-alone momentum pass (remove_CM_motion! before the first step): same reduction, no kick
+template <typename T>
+__global__ void clear_cm_kernel(CmState<T>* cm) {
+    cm->v[0] = cm->v[1] = cm->v[2] = (T)0;
+    cm->valid = 0;
+}
+
+// ---- Andersen thermostat (src/coupling.jl:184-212; GPU kernel src/kernels.jl:705-721) -----------
+// Each atom independently, with probability p per step, gets a velocity drawn from the
+// Maxwell-Boltzmann distribution, sigma_v = sqrt(kT/m). Philox4x32-10 keyed by (key, ctr1), counter
+// = atom index (original order, 1-based as in the reference) so the stream does not depend on the slot
+// order; normals by Box-Muller. Statistical parity only (the reference's normal transform lives in
+// the un-vendored PhiloxRNG.jl). Consumes the pending v_cm.
+template <typename T>
+__global__ void andersen_kernel(int n, T kT, double prob, uint32_t ctr1_lo, uint32_t ctr1_hi, uint32_t key_lo,
+                                uint32_t key_hi, uint32_t step_lo, const int* __restrict__ orig,
+                                const T* __restrict__ mass, typename VT<T>::T4* __restrict__ vel4,
+                                CmState<T>* __restrict__ cm, Control* __restrict__ ctl) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) {
+        typename VT<T>::T4 v = vel4[s];
+        if (cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
+        uint32_t c[4] = {(uint32_t)(orig[s] + 1), step_lo, ctr1_lo, ctr1_hi};
+        philox4x32_10(c, key_lo, key_hi);
+        double u = ((double)c[0] * 4294967296.0 + (double)c[1]) * (1.0 / 18446744073709551616.0);
+        if (u < prob) {
+            uint32_t d[4] = {(uint32_t)(orig[s] + 1 + n), step_lo, ctr1_lo, ctr1_hi};
+            philox4x32_10(d, key_lo, key_hi);
+            const double two_pi = 6.283185307179586;
+            double u1 = ((double)d[0] + 1.0) * (1.0 / 4294967296.0), u2 = (double)d[1] * (1.0 / 4294967296.0);
+            double u3 = ((double)d[2] + 1.0) * (1.0 / 4294967296.0), u4 = (double)d[3] * (1.0 / 4294967296.0);
+            double r1 = sqrt(-2.0 * log(u1)), r2 = sqrt(-2.0 * log(u3));
+            T m = mass[s];
+            double sd = (m > (T)0) ? sqrt((double)kT / (double)m) : 0.0;
+            v.x = (T)(sd * r1 * cos(two_pi * u2));
+            v.y = (T)(sd * r1 * sin(two_pi * u2));
+            v.z = (T)(sd * r2 * cos(two_pi * u4));
+        }
+        vel4[s] = v;
+    }
+    // last CTA clears the pending CM state
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicInc(&ctl->ticket, gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) cm->valid = 0;
+}
+
+// kinetic energy: 1/2 sum m v.v (src/energy.jl:56-70), partials per CTA then host sum
+template <typename T>
+__global__ void kinetic_kernel(int n, const T* __restrict__ vels, const T* __restrict__ mass, double* __restrict__ partial) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double k = 0;
+    if (i < n) {
+        double vx = vels[3 * (size_t)i], vy = vels[3 * (size_t)i + 1], vz = vels[3 * (size_t)i + 2];
+        k = 0.5 * (double)mass[i] * (vx * vx + vy * vy + vz * vz);
+    }
+    __shared__ double s_red[32];
+    for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = k;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += s_red[w];
+        partial[blockIdx.x] = s;
+    }
+}
+
+// sum(m v) partials over an original-order velocity array (mb_remove_cm_motion)
+template <typename T>
+__global__ void momentum_kernel(int n, const T* __restrict__ vels, const T* __restrict__ mass, double* __restrict__ partial) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double p[3] = {0, 0, 0};
+    if (i < n) {
+        T m = mass[i];
+        for (int d = 0; d < 3; d++) p[d] = (double)(vels[3 * (size_t)i + d] * m);
+    }
+    __shared__ double s_red[32][3];
+    for (int d = 0; d < 3; d++)
+        for (int o = 16; o > 0; o >>= 1) p[d] += __shfl_xor_sync(0xffffffffu, p[d], o);
+    if ((threadIdx.x & 31) == 0)
+        for (int d = 0; d < 3; d++) s_red[threadIdx.x >> 5][d] = p[d];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[3] = {0, 0, 0};
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++)
+            for (int d = 0; d < 3; d++) s[d] += s_red[w][d];
+        for (int d = 0; d < 3; d++) partial[3 * (size_t)blockIdx.x + d] = s[d];
+    }
+}
+template <typename T>
+__global__ void subtract_velocity_kernel(int n, T vx, T vy, T vz, T* __restrict__ vels) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vels[3 * (size_t)i] -= vx;
+    vels[3 * (size_t)i + 1] -= vy;
+    vels[3 * (size_t)i + 2] -= vz;
+}
+
+}  // namespace mb

@@ -1,0 +1,20 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "tests"), ROOT):
+    if p in sys.path:
+        sys.path.remove(p)
+    sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden_6mrr():
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "6mrr.npz")))

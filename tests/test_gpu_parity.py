@@ -1,0 +1,369 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs,
+against the reference's golden vectors (tests/golden), and size-independent properties at full size.
+
+Tolerances (stated per quantity):
+  f64: per-atom force |dF| <= 1e-9 * max|F| + 1e-9 ; energy rel 1e-11 — same arithmetic, different order
+       (the reference's own CPU-vs-GPU bar is rtol 1e-8, test/gpu_consistency.jl:43-49)
+  f32: per-atom force |dF| <= 5e-5 * max|F| + 2e-3 kJ/mol/nm ; energy rel 2e-6 vs the f64 oracle on the
+       same f32-rounded inputs (the reference accepts 5e-4 kJ/mol on E and 1e-4 nm on coords for its f32
+       GPU path, test/simulation.jl:1246-1252)
+  OpenMM goldens (6mrr, f64): max |dF| < 1e-7 kJ/mol/nm, |dE| < 1e-5 kJ/mol (test/protein.jl:263-275)
+"""
+import numpy as np
+import pytest
+
+import mbhelpers as H
+import mollyb200 as mb
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(dtype, fmax):
+    return (1e-9 * fmax + 1e-9) if np.dtype(dtype) == np.float64 else (5e-5 * fmax + 2e-3)
+
+
+def _etol(dtype, e):
+    return (1e-11 if np.dtype(dtype) == np.float64 else 2e-6) * max(abs(e), 1.0)
+
+
+def _check(sysd, mb_inters, o_inters, dtype, r_list=0.0, expect_path=None, label=""):
+    xin = sysd["coords"].astype(dtype)
+    sd = dict(sysd, coords=xin)
+    s = H.make_system(sd, mb_inters, dtype, r_list=r_list)
+    orc = H.make_oracle(sd, o_inters, dtype=np.float64)
+    f_ref, e_ref, vir_ref = orc.forces_allpairs(xin.astype(np.float64), virial=True)
+    f = mb.forces(s)
+    e = mb.potential_energy(s)
+    f2, vir = mb.forces_virial(s)
+    st = s.stats()
+    if expect_path is not None:
+        assert st["path"] == expect_path, st
+    fmax = np.abs(f_ref).max()
+    err = np.abs(f.astype(np.float64) - f_ref).max()
+    print(f"[{label}] n={sysd['n']} dtype={np.dtype(dtype).name} path={st['path']} bricks={st['n_bricks']} "
+          f"brick={st['brick_dims']} stride={st['list_stride']} maxnb={st['max_neighbors']} halo={st['max_halo']} "
+          f"max|dF|={err:.3e} (max|F|={fmax:.3e}) dE={e - e_ref:.3e} (E={e_ref:.6e})")
+    assert err <= _tol(dtype, fmax)
+    assert abs(e - e_ref) <= _etol(dtype, e_ref)
+    assert np.array_equal(f, f2)  # deterministic: same kernel, no atomics
+    vtol = (1e-9 if np.dtype(dtype) == np.float64 else 1e-4) * max(np.abs(vir_ref).max(), 1.0)
+    assert np.abs(vir.astype(np.float64) - vir_ref).max() <= vtol
+    s.close()
+    return f, e
+
+
+# ---------------------------------------------------------------------------------------------------
+# all-pairs path (config 1 semantics)
+# ---------------------------------------------------------------------------------------------------
+def test_pair_known_answers_through_abi():
+    # test/interactions.jl:61-82, :374-395 evaluated by the CUDA kernels
+    def pair(inter, r, q=0.0):
+        atoms = mb.atoms_from_arrays([10, 10], [q, q], [0.3, 0.3], [0.2, 0.2], np.float64)
+        s = mb.System(atoms=atoms, coords=np.array([[1.0, 1, 1], [1.0 + r, 1, 1]]), boundary=mb.CubicBoundary(5.0),
+                      pairwise_inters=(inter,), dtype=np.float64)
+        f, e = mb.forces(s)[1, 0], mb.potential_energy(s)
+        s.close()
+        return f, e
+    f, e = pair(mb.LennardJones(), 0.3)
+    assert abs(f - 16.0) < 1e-9 and abs(e) < 1e-9
+    f, e = pair(mb.LennardJones(), 0.4)
+    assert abs(f + 1.375509739) < 1e-9 and abs(e + 0.1170417309) < 1e-9
+    f, e = pair(mb.Coulomb(), 0.3, 1.0)
+    assert abs(f - 1543.727311) < 1e-5 and abs(e - 463.1181933) < 1e-5
+    f, e = pair(mb.CoulombReactionField(dist_cutoff=1.0), 1.2, 1.0)
+    assert f == 0.0 and e == 0.0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_readme_system_allpairs(dtype):
+    sd = H.readme_system(100, 2.0, seed=1)
+    _check(sd, (mb.LennardJones(),), [o.Inter(o.LJ)], dtype, expect_path=0, label="C1 readme")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("cut", ["distance", "shifted_potential", "shifted_force"])
+def test_molecular_allpairs_exceptions(dtype, cut):
+    sd = H.molecular_system(150, [3.0, 3.2, 3.4], seed=11)
+    mcut = {"distance": mb.DistanceCutoff, "shifted_potential": mb.ShiftedPotentialCutoff,
+            "shifted_force": mb.ShiftedForceCutoff}[cut](1.2)
+    ocut = {"distance": o.CUT_DISTANCE, "shifted_potential": o.CUT_SHIFTED_POTENTIAL,
+            "shifted_force": o.CUT_SHIFTED_FORCE}[cut]
+    _check(sd, (mb.LennardJones(cutoff=mcut, weight_special=0.5), mb.Coulomb(cutoff=mcut, weight_special=0.8333)),
+           [o.Inter(o.LJ, ocut, 1.2, weight_special=0.5), o.Inter(o.COULOMB, ocut, 1.2, weight_special=0.8333)],
+           dtype, expect_path=0, label=f"molecular all-pairs {cut}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# brick / neighbour-list path
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("cells", [6, 9])
+def test_lj_fluid_brick_path(dtype, cells):
+    sd = H.lj_fluid(cells, seed=42, dtype=np.float64)  # 864 / 2916 atoms at the C2 density, rc 1.2 nm
+    rc = 1.2 if cells >= 9 else 0.9
+    _check(sd, (mb.LennardJones(cutoff=mb.DistanceCutoff(rc), use_neighbors=True),),
+           [o.Inter(o.LJ, o.CUT_DISTANCE, rc, use_neighbors=True)], dtype, r_list=rc + 0.1, expect_path=1,
+           label=f"LJ fluid {cells}")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_lj_fluid_16k(dtype):
+    sd = H.lj_fluid(16, seed=42, dtype=np.float64)  # 16384 atoms, box 9.19 nm
+    _check(sd, (mb.LennardJones(cutoff=mb.DistanceCutoff(1.2), use_neighbors=True),),
+           [o.Inter(o.LJ, o.CUT_DISTANCE, 1.2, use_neighbors=True)], dtype, r_list=1.3, expect_path=1, label="LJ 16k")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("coul", ["crf", "coulomb_sf", "ewald"])
+def test_molecular_brick_path(dtype, coul):
+    sd = H.molecular_system(1500, [4.1, 4.4, 4.8], seed=5)  # 6000 atoms, orthorhombic, mixed types, charges
+    lj_m = mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True, weight_special=0.5)
+    lj_o = o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=0.5, use_neighbors=True)
+    if coul == "crf":
+        c_m = mb.CoulombReactionField(dist_cutoff=1.0, use_neighbors=True, weight_special=0.8333)
+        c_o = o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=0.8333, use_neighbors=True)
+    elif coul == "coulomb_sf":
+        c_m = mb.Coulomb(cutoff=mb.ShiftedForceCutoff(1.0), use_neighbors=True, weight_special=0.8333)
+        c_o = o.Inter(o.COULOMB, o.CUT_SHIFTED_FORCE, 1.0, weight_special=0.8333, use_neighbors=True)
+    else:
+        c_m = mb.CoulombEwald(dist_cutoff=1.0, use_neighbors=True, weight_special=0.8333)
+        alpha = float(np.sqrt(-np.log(2 * 5e-4)) / 1.0)
+        c_o = o.Inter(o.EWALD_REAL, o.CUT_DISTANCE, 1.0, weight_special=0.8333, ewald_alpha=alpha, use_neighbors=True)
+    _check(sd, (lj_m, c_m), [lj_o, c_o], dtype, r_list=1.1, expect_path=1, label=f"molecular brick {coul}")
+
+
+@pytest.mark.parametrize("name", ["lj_only", "coul_only"])
+def test_6mrr_openmm_golden_f64(golden_6mrr, name):
+    """The reference's own GPU bar (test/protein.jl:356-360): CUDA f64 vs OpenMM Reference platform."""
+    g = golden_6mrr
+    box = g["box"]
+    x = g["coords"] - np.floor(g["coords"] / box) * box
+    if name == "lj_only":
+        inter = mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True, weight_special=float(g["lj14scale"]))
+    else:
+        inter = mb.CoulombReactionField(dist_cutoff=1.0, use_neighbors=True, weight_special=float(g["coulomb14scale"]))
+    atoms = mb.atoms_from_arrays(g["mass"], g["charge"], g["sigma"], g["eps"], np.float64)
+    nf = mb.GPUNeighborFinder(dist_cutoff=1.2, excluded_pairs=g["excluded"] + 1, special_pairs=g["special"] + 1)
+    s = mb.System(atoms=atoms, coords=x, boundary=mb.CubicBoundary(*box), pairwise_inters=(inter,), neighbor_finder=nf,
+                  dtype=np.float64)
+    f = mb.forces(s)
+    e = mb.potential_energy(s)
+    st = s.stats()
+    if name == "lj_only":
+        e += o.lj_dispersion_correction_energy(g["sigma"], g["eps"], box, 1.0)  # general interaction, host scalar
+    err = np.linalg.norm(f - g[f"forces_{name}"], axis=1).max()
+    print(f"[6mrr {name}] path={st['path']} brick={st['brick_dims']} maxnb={st['max_neighbors']} "
+          f"pairs={st['n_pairs_in_list']} max|dF|={err:.3e} dE={e - float(g[f'energy_{name}']):.3e}")
+    assert st["path"] == 1
+    assert err < 1e-7
+    assert abs(e - float(g[f"energy_{name}"])) < 1e-5
+    if name == "lj_only":
+        # full-shell list at 1.2 nm holds every eligible pair twice: 2 x 4 602 420 (test/basic.jl:592)
+        assert st["n_pairs_in_list"] == 2 * 4602420
+    s.close()
+
+
+def test_6mrr_f32_vs_oracle(golden_6mrr):
+    g = golden_6mrr
+    box = g["box"]
+    x = (g["coords"] - np.floor(g["coords"] / box) * box).astype(np.float32)
+    sd = dict(n=len(x), box=box, coords=x, velocities=g["velocities_300K"], mass=g["mass"], charge=g["charge"],
+              sigma=g["sigma"], eps=g["eps"], excluded=g["excluded"], special=g["special"])
+    _check(sd, (mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True, weight_special=0.5),
+                mb.CoulombReactionField(dist_cutoff=1.0, use_neighbors=True, weight_special=float(g["coulomb14scale"]))),
+           [o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=0.5, use_neighbors=True),
+            o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=float(g["coulomb14scale"]), use_neighbors=True)],
+           np.float32, r_list=1.15, expect_path=1, label="6mrr LJ+CRF f32")
+
+
+def test_forces_track_moving_coordinates_and_rebuild():
+    """Buffer reuse across calls (test/gpu_consistency.jl:451-492): move atoms a little (no rebuild), then a lot
+    (forces a rebuild), including periodic wrapping by the caller."""
+    sd = H.lj_fluid(9, seed=5, dtype=np.float64)
+    inter_m = (mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True),)
+    inter_o = [o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, use_neighbors=True)]
+    s = H.make_system(sd, inter_m, np.float64, r_list=1.2)
+    orc = H.make_oracle(sd, inter_o)
+    rng = np.random.default_rng(0)
+    x = sd["coords"].copy()
+    rebuilds = []
+    for it, amp in enumerate([0.0, 0.01, 0.01, 0.3, 0.01]):
+        x = x + rng.normal(0, amp, x.shape) if amp else x
+        x = x - np.floor(x / sd["box"]) * sd["box"]  # caller wraps, atoms jump across the box
+        s.coords = x.copy()
+        f = mb.forces(s)
+        f_ref, _, _ = orc.forces_allpairs(x)
+        assert np.abs(f - f_ref).max() <= 1e-9 * np.abs(f_ref).max() + 1e-9, it
+        rebuilds.append(s.stats()["n_rebuilds"])
+    print("rebuild counts:", rebuilds)
+    assert rebuilds[1] == rebuilds[0] and rebuilds[3] > rebuilds[2]
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# VelocityVerlet
+# ---------------------------------------------------------------------------------------------------
+def _pos_err(a, b, box):
+    d = a.astype(np.float64) - b.astype(np.float64)
+    d -= box * np.round(d / box)
+    return np.abs(d).max()
+
+
+@pytest.mark.parametrize("policy", [0, 10])
+def test_vv_lj_fluid_f64_matches_oracle(policy):
+    sd = H.lj_fluid(9, seed=7, dtype=np.float64, temp=120.0)
+    rc, rl, dt, n = 1.0, 1.2, 0.002, 60
+    s = H.make_system(sd, (mb.LennardJones(cutoff=mb.DistanceCutoff(rc), use_neighbors=True),), np.float64, r_list=rl,
+                      n_steps=policy)
+    orc = H.make_oracle(sd, [o.Inter(o.LJ, o.CUT_DISTANCE, rc, use_neighbors=True)])
+    x_ref, v_ref, _ = orc.simulate_vv(sd["coords"], sd["velocities"], dt, n, remove_cm_every=1, r_list=rl, nl_every=10)
+    mb.simulate(s, mb.VelocityVerlet(dt=dt), n)
+    st = s.stats()
+    ex, ev = _pos_err(s.coords, x_ref, sd["box"]), np.abs(s.velocities - v_ref).max()
+    print(f"[VV LJ f64 policy={policy}] rebuilds={st['n_rebuilds']} violations={st['violations']} dx={ex:.3e} dv={ev:.3e}")
+    # a DistanceCutoff force is discontinuous at rc, so pairs crossing the cutoff amplify rounding; bars follow
+    # test/simulation.jl:1246-1252 (1e-4 nm) tightened for f64
+    assert ex < 1e-7 and ev < 1e-5
+    assert (s.coords >= 0).all() and (s.coords < sd["box"]).all()
+    assert np.abs((sd["mass"][:, None] * s.velocities).sum(0)).max() < 1e-8
+    if policy == 0:
+        assert st["n_rebuilds"] >= 2 and st["violations"] == 0
+    s.close()
+
+
+def test_vv_molecular_f64_matches_oracle():
+    sd = H.molecular_system(1500, [4.1, 4.4, 4.8], seed=5)
+    lj_m = mb.LennardJones(cutoff=mb.ShiftedForceCutoff(1.0), use_neighbors=True, weight_special=0.5)
+    c_m = mb.CoulombReactionField(dist_cutoff=1.0, use_neighbors=True, weight_special=0.8333)
+    lj_o = o.Inter(o.LJ, o.CUT_SHIFTED_FORCE, 1.0, weight_special=0.5, use_neighbors=True)
+    c_o = o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=0.8333, use_neighbors=True)
+    s = H.make_system(sd, (lj_m, c_m), np.float64, r_list=1.15)
+    orc = H.make_oracle(sd, [lj_o, c_o])
+    dt, n = 0.0005, 40
+    x_ref, v_ref, _ = orc.simulate_vv(sd["coords"], sd["velocities"], dt, n, remove_cm_every=1, r_list=1.15, nl_every=5)
+    mb.simulate(s, mb.VelocityVerlet(dt=dt), n)
+    ex, ev = _pos_err(s.coords, x_ref, sd["box"]), np.abs(s.velocities - v_ref).max()
+    print(f"[VV molecular f64] dx={ex:.3e} dv={ev:.3e} rebuilds={s.stats()['n_rebuilds']}")
+    assert ex < 1e-7 and ev < 1e-4
+    s.close()
+
+
+def test_vv_readme_allpairs_f64():
+    sd = H.readme_system(100, 2.0, seed=1)
+    s = H.make_system(sd, (mb.LennardJones(),), np.float64)
+    orc = H.make_oracle(sd, [o.Inter(o.LJ)])
+    x_ref, v_ref, _ = orc.simulate_vv(sd["coords"], sd["velocities"], 0.002, 100, remove_cm_every=1, r_list=0.0)
+    mb.simulate(s, mb.VelocityVerlet(dt=0.002), 100)
+    ex, ev = _pos_err(s.coords, x_ref, sd["box"]), np.abs(s.velocities - v_ref).max()
+    print(f"[VV readme f64] dx={ex:.3e} dv={ev:.3e}")
+    assert ex < 1e-9 and ev < 1e-8
+    s.close()
+
+
+def test_vv_f32_tracks_f64_oracle():
+    sd = H.lj_fluid(9, seed=7, dtype=np.float64, temp=90.0)
+    rc, rl, dt, n = 1.0, 1.2, 0.002, 50
+    s = H.make_system(sd, (mb.LennardJones(cutoff=mb.ShiftedForceCutoff(rc), use_neighbors=True),), np.float32, r_list=rl)
+    orc = H.make_oracle(dict(sd, coords=sd["coords"].astype(np.float32), velocities=sd["velocities"].astype(np.float32)),
+                        [o.Inter(o.LJ, o.CUT_SHIFTED_FORCE, rc, use_neighbors=True)])
+    x_ref, v_ref, _ = orc.simulate_vv(sd["coords"].astype(np.float32), sd["velocities"].astype(np.float32), dt, n,
+                                      remove_cm_every=1, r_list=rl, nl_every=10)
+    mb.simulate(s, mb.VelocityVerlet(dt=dt), n)
+    ex = _pos_err(s.coords, x_ref, sd["box"])
+    print(f"[VV LJ f32] dx={ex:.3e}")
+    assert ex < 1e-4  # test/simulation.jl:1251
+    s.close()
+
+
+def test_vv_chunked_equals_single_call():
+    """simulate!(n1) then simulate!(n2; init_step=n1) == simulate!(n1+n2) (state fully round-trips through the ABI)."""
+    sd = H.lj_fluid(6, seed=3, dtype=np.float64)
+    mk = lambda: H.make_system(sd, (mb.LennardJones(cutoff=mb.ShiftedForceCutoff(0.9), use_neighbors=True),),
+                               np.float64, r_list=1.0)
+    a, b = mk(), mk()
+    mb.simulate(a, mb.VelocityVerlet(dt=0.002), 40)
+    mb.simulate(b, mb.VelocityVerlet(dt=0.002), 25)
+    mb.simulate(b, mb.VelocityVerlet(dt=0.002), 15, init_step=25)
+    assert _pos_err(a.coords, b.coords, sd["box"]) < 1e-9
+    assert np.abs(a.velocities - b.velocities).max() < 1e-8
+    a.close(); b.close()
+
+
+def test_andersen_thermostat_statistics():
+    # test/coupling.jl:67-98: 9.5 K < <T> < 10.5 K, std < 1 K (here 2916 atoms, shorter run)
+    sd = H.lj_fluid(9, seed=11, dtype=np.float64, temp=10.0)
+    s = H.make_system(sd, (mb.LennardJones(cutoff=mb.ShiftedForceCutoff(1.0), use_neighbors=True),), np.float32, r_list=1.2)
+    sim = mb.VelocityVerlet(dt=0.002, coupling=mb.AndersenThermostat(10.0, 0.1))
+    temps = []
+    rng = np.random.default_rng(1)
+    mb.simulate(s, sim, 300, rng=rng)
+    for k in range(20):
+        mb.simulate(s, sim, 25, init_step=300 + 25 * k, rng=rng)
+        temps.append(mb.temperature(s))
+    print(f"[Andersen] <T>={np.mean(temps):.3f} std={np.std(temps):.3f}")
+    assert 9.5 < np.mean(temps) < 10.5 and np.std(temps) < 1.0
+    s.close()
+
+
+def test_kinetic_energy_and_cm(golden_6mrr):
+    g = golden_6mrr
+    atoms = mb.atoms_from_arrays(g["mass"], g["charge"], g["sigma"], g["eps"], np.float64)
+    s = mb.System(atoms=atoms, coords=g["coords"], boundary=mb.CubicBoundary(*g["box"]), velocities=g["velocities_300K"],
+                  pairwise_inters=(mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True),),
+                  neighbor_finder=mb.GPUNeighborFinder(dist_cutoff=1.2), dtype=np.float64)
+    assert abs(mb.kinetic_energy(s) - 65521.87288132431) < 1.5e-8 * 65521.87288132431  # test/protein.jl:284
+    assert abs(mb.temperature(s) - 329.3202932884933) < 1.5e-8 * 329.3202932884933
+    mb.remove_CM_motion(s)
+    assert np.abs((g["mass"][:, None] * s.velocities).sum(0)).max() < 1e-8
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE config 2: 256 000 atoms, f32, rc 1.2 nm)
+# ---------------------------------------------------------------------------------------------------
+def test_c2_full_size_properties():
+    sd = H.lj_fluid(40, seed=42, dtype=np.float32)
+    assert sd["n"] == 256000
+    inter = (mb.LennardJones(cutoff=mb.DistanceCutoff(1.2), use_neighbors=True),)
+    s = H.make_system(sd, inter, np.float32, r_list=1.3)
+    f = mb.forces(s)
+    e = mb.potential_energy(s)
+    st = s.stats()
+    print(f"[C2] bricks={st['n_bricks']} brick={st['brick_dims']} stride={st['list_stride']} maxnb={st['max_neighbors']} "
+          f"halo={st['max_halo']} pairs/atom={st['n_pairs_in_list'] / sd['n']:.1f} E={e:.6e}")
+    # Newton's third law: forces sum to zero up to f32 rounding
+    assert np.abs(f.astype(np.float64).sum(0)).max() < 1e-4 * np.abs(f).max() * np.sqrt(sd["n"])
+    # determinism
+    assert np.array_equal(f, mb.forces(s))
+    # sampled parity: oracle forces on 64 atoms via a 20 000-atom neighbourhood is expensive; use translation
+    # invariance instead: shifting every atom by the same vector (mod box) leaves forces unchanged up to rounding
+    shift = np.array([3.3, -7.1, 11.9], np.float32)
+    x2 = sd["coords"] + shift
+    x2 = (x2 - np.floor(x2 / sd["box"]) * sd["box"]).astype(np.float32)
+    s2 = H.make_system(dict(sd, coords=x2), inter, np.float32, r_list=1.3)
+    f2 = mb.forces(s2)
+    assert np.abs(f2 - f).max() < 2e-3 * np.abs(f).max()
+    # permutation invariance: relabelling atoms permutes the forces
+    perm = np.random.default_rng(0).permutation(sd["n"])
+    s3 = H.make_system(dict(sd, coords=sd["coords"][perm]), inter, np.float32, r_list=1.3)
+    f3 = mb.forces(s3)
+    assert np.abs(f3 - f[perm]).max() < 1e-4 * np.abs(f).max()
+    # pair count: in-cutoff neighbours per atom for rho = 21.105 nm^-3, r_list 1.3 -> 4/3 pi r^3 rho = 194.2
+    assert abs(st["n_pairs_in_list"] / sd["n"] - 194.2) < 3.0
+    for q in (s, s2, s3):
+        q.close()
+
+
+def test_c2_energy_conservation_f32():
+    """NVE drift over 200 steps at full size with a shifted-force cutoff (continuous force)."""
+    sd = H.lj_fluid(40, seed=42, dtype=np.float32)
+    s = H.make_system(sd, (mb.LennardJones(cutoff=mb.ShiftedForceCutoff(1.2), use_neighbors=True),), np.float32, r_list=1.3)
+    e0 = mb.potential_energy(s) + mb.kinetic_energy(s)
+    mb.simulate(s, mb.VelocityVerlet(dt=0.002), 200)
+    e1 = mb.potential_energy(s) + mb.kinetic_energy(s)
+    ke = mb.kinetic_energy(s)
+    st = s.stats()
+    print(f"[C2 NVE] E0={e0:.4f} E1={e1:.4f} drift={(e1 - e0) / sd['n']:.3e} kJ/mol/atom KE={ke:.2f} rebuilds={st['n_rebuilds']}")
+    assert abs(e1 - e0) / sd["n"] < 2e-3  # ~0.3 % of kT per atom at 90 K
+    s.close()

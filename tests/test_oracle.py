@@ -1,0 +1,159 @@
+"""CPU tests: pin the oracle against the reference's own known answers and golden vectors
+(SURVEY.md §4 / §8c). No GPU needed."""
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+import mbhelpers as H
+
+
+def _pair(inter, r, q=0.0, dtype=np.float64, sig=0.3, eps=0.2, box=5.0):
+    s = o.OracleSystem(box=[box] * 3, mass=[10, 10], charge=[q, q], sigma=[sig, sig], eps=[eps, eps], inters=[inter],
+                       dtype=dtype)
+    x = np.array([[1.0, 1.0, 1.0], [1.0 + r, 1.0, 1.0]])
+    f, pe, _ = s.forces_allpairs(x, n_threads=1)
+    return f[1, 0], pe  # +x force on atom j = F (positive = repulsive)
+
+
+def test_mic_and_wrap_known_answers():
+    # test/basic.jl:2-38
+    assert o.vector_1D(4.0, 6.0, 10.0) == 2.0
+    assert o.vector_1D(1.0, 9.0, 10.0) == -2.0
+    assert o.wrap_coord_1D(-2.0, 10.0) == 8.0
+    assert o.wrap_coord_1D(12.0, 10.0) == 2.0
+    box = (10.0, 5.0, 3.5)
+    v = [o.vector_1D(a, b, L) for a, b, L in zip((4.0, 1.0, 1.0), (6.0, 4.0, 3.0), box)]
+    assert v == [2.0, -2.0, -1.5]
+
+
+def test_lj_pair_known_answers():
+    # test/interactions.jl:61-82 (sigma 0.3, eps 0.2)
+    lj = o.Inter(o.LJ)
+    f, e = _pair(lj, 0.3)
+    assert abs(f - 16.0) < 1e-9 and abs(e - 0.0) < 1e-9
+    f, e = _pair(lj, 0.4)
+    assert abs(f - (-1.375509739)) < 1e-9 and abs(e - (-0.1170417309)) < 1e-9
+
+
+def test_coulomb_pair_known_answers():
+    # test/interactions.jl:374-395 (q = 1, 1), atol 1e-5
+    c = o.Inter(o.COULOMB)
+    f, e = _pair(c, 0.3, q=1.0)
+    assert abs(f - 1543.727311) < 1e-5 and abs(e - 463.1181933) < 1e-5
+    f, e = _pair(c, 0.4, q=1.0)
+    assert abs(f - 868.3466125) < 1e-5 and abs(e - 347.338645) < 1e-5
+
+
+def test_mixing_rules():
+    # test/interactions.jl:15-21: Lorentz sigma of (0.2, 0.3) = 0.25; geometric eps of (0.1, 0.2)
+    s = o.OracleSystem(box=[5.0] * 3, mass=[1, 1], charge=[0, 0], sigma=[0.2, 0.3], eps=[0.1, 0.2],
+                       inters=[o.Inter(o.LJ)])
+    x = np.array([[1.0, 1, 1], [1.25, 1, 1]])  # r = sigma_mixed -> E = 0
+    _, pe, _ = s.forces_allpairs(x, n_threads=1)
+    assert abs(pe) < 1e-12
+    x = np.array([[1.0, 1, 1], [1.0 + 0.25 * 2 ** (1 / 6), 1, 1]])  # minimum: E = -eps_mixed
+    _, pe, _ = s.forces_allpairs(x, n_threads=1)
+    assert abs(pe + 0.14142135623730953) < 1e-12
+
+
+def test_crf_behaviour():
+    # test/interactions.jl:506-660: zero beyond cutoff; special pairs = weighted plain Coulomb
+    crf = o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=0.5)
+    f, e = _pair(crf, 1.2, q=1.0)
+    assert f == 0.0 and e == 0.0
+    s = o.OracleSystem(box=[5.0] * 3, mass=[1, 1], charge=[1.0, 1.0], sigma=[0, 0], eps=[0, 0], inters=[crf],
+                       special_pairs=np.array([[0, 1]]))
+    x = np.array([[1.0, 1, 1], [1.4, 1, 1]])
+    f, pe, _ = s.forces_allpairs(x, n_threads=1)
+    assert abs(f[1, 0] - 0.5 * 868.34661025) < 1e-6 and abs(pe - 0.5 * 347.3386441) < 1e-6
+    # eps = inf: k_rf = 1/(2 rc^3)
+    crf_inf = o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, solvent_dielectric=float("inf"))
+    f, e = _pair(crf_inf, 0.5, q=1.0)
+    ke = o.COULOMB_CONST
+    assert abs(f - ke * (1 / 0.25 - 2 * 0.5 * 0.5)) < 1e-9
+    assert abs(e - ke * (1 / 0.5 + 0.5 * 0.25 - 1.5)) < 1e-9
+
+
+def test_cutoff_algebra():
+    # test/interactions.jl:1574-1635 relations: shifted potential is continuous at rc, shifted force has F(rc)=0
+    for kind in (o.LJ, o.COULOMB):
+        q = 1.0 if kind == o.COULOMB else 0.0
+        plain = o.Inter(kind, o.CUT_DISTANCE, 0.8)
+        sp = o.Inter(kind, o.CUT_SHIFTED_POTENTIAL, 0.8)
+        sf = o.Inter(kind, o.CUT_SHIFTED_FORCE, 0.8)
+        f0, e0 = _pair(plain, 0.5, q)
+        f1, e1 = _pair(sp, 0.5, q)
+        f2, e2 = _pair(sf, 0.5, q)
+        fc, ec = _pair(plain, 0.8, q)
+        assert abs(f1 - f0) < 1e-12 and abs(e1 - (e0 - ec)) < 1e-12
+        assert abs(f2 - (f0 - fc)) < 1e-12 and abs(e2 - (e0 + (0.5 - 0.8) * fc - ec)) < 1e-12
+        fe, ee = _pair(sf, 0.8 - 1e-12, q)
+        assert abs(fe) < 1e-6 and abs(ee) < 1e-9
+        assert _pair(sf, 0.81, q) == (0.0, 0.0)
+
+
+def test_6mrr_pair_count(golden_6mrr):
+    # test/basic.jl:592-593: exactly 4 602 420 eligible pairs within 1.2 nm
+    g = golden_6mrr
+    s = o.OracleSystem(box=g["box"], mass=g["mass"], charge=g["charge"], sigma=g["sigma"], eps=g["eps"],
+                       inters=[o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, use_neighbors=True)], excluded_pairs=g["excluded"],
+                       special_pairs=g["special"])
+    x = g["coords"] - np.floor(g["coords"] / g["box"]) * g["box"]
+    nl = s.neighbor_list(x, 1.2)
+    assert len(nl) == 4602420
+    assert int(nl[:, 2].sum()) == len(g["special"])
+
+
+@pytest.mark.parametrize("name", ["lj_only", "coul_only"])
+def test_6mrr_openmm_golden(golden_6mrr, name):
+    # test/protein.jl:206-276: max |dF| < 1e-7 kJ/mol/nm, |dE| < 1e-5 kJ/mol vs OpenMM Reference platform
+    g = golden_6mrr
+    if name == "lj_only":
+        inter = o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=float(g["lj14scale"]), use_neighbors=True)
+    else:
+        inter = o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=float(g["coulomb14scale"]), use_neighbors=True)
+    s = o.OracleSystem(box=g["box"], mass=g["mass"], charge=g["charge"], sigma=g["sigma"], eps=g["eps"], inters=[inter],
+                       excluded_pairs=g["excluded"], special_pairs=g["special"])
+    x = g["coords"] - np.floor(g["coords"] / g["box"]) * g["box"]
+    f, pe, _ = s.forces_allpairs(x)
+    if name == "lj_only":
+        pe += o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
+    assert np.linalg.norm(f - g[f"forces_{name}"], axis=1).max() < 1e-7
+    assert abs(pe - float(g[f"energy_{name}"])) < 1e-5
+    # neighbour-list path of the oracle agrees with brute force
+    nl = s.neighbor_list(x, 1.0 + 0.2)
+    f2, pe2, _ = s.forces_nl(x, nl)
+    assert np.abs(f2 - f).max() < 1e-8
+    if name == "lj_only":
+        pe2 += o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
+    assert abs(pe2 - pe) < 1e-7
+
+
+def test_6mrr_kinetic_energy_and_temperature(golden_6mrr):
+    # test/protein.jl:284-286
+    g = golden_6mrr
+    ke = o.kinetic_energy(g["mass"], g["velocities_300K"])
+    # the reference uses isapprox (rtol = sqrt(eps) = 1.5e-8)
+    assert abs(ke - 65521.87288132431) < 1.5e-8 * 65521.87288132431
+    assert abs(o.temperature(g["mass"], g["velocities_300K"]) - 329.3202932884933) < 1.5e-8 * 329.3202932884933
+
+
+def test_vv_oracle_conserves_energy_and_momentum():
+    sd = H.lj_fluid(4, seed=3, dtype=np.float64)  # 256 atoms
+    inter = o.Inter(o.LJ, o.CUT_SHIFTED_FORCE, 1.0, use_neighbors=True)
+    s = H.make_oracle(sd, [inter])
+    x0, v0 = sd["coords"], sd["velocities"]
+    _, pe0, _ = s.forces_allpairs(x0)
+    e0 = pe0 + o.kinetic_energy(sd["mass"], v0)
+    x1, v1, pe1 = s.simulate_vv(x0, v0, 0.002, 200, remove_cm_every=1, r_list=1.2, nl_every=10)
+    e1 = pe1 + o.kinetic_energy(sd["mass"], v1)
+    assert abs(e1 - e0) < 5e-3 * abs(e0) / 100 + 0.05
+    assert np.abs((sd["mass"][:, None] * v1).sum(0)).max() < 1e-9
+    assert (x1 >= 0).all() and (x1 < sd["box"]).all()
+    # f32 instantiation tracks f64
+    s32 = H.make_oracle(sd, [inter], dtype=np.float32)
+    x2, v2, _ = s32.simulate_vv(x0, v0, 0.002, 20, r_list=1.2)
+    x3, v3, _ = s.simulate_vv(x0, v0, 0.002, 20, r_list=1.2)
+    d = x2.astype(np.float64) - x3
+    d -= sd["box"] * np.round(d / sd["box"])
+    assert np.abs(d).max() < 1e-4
