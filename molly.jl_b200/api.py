@@ -300,7 +300,8 @@ class System:
 
     def stats(self) -> dict:
         st = capi.MBStats()
-        capi.check(self._L.mb_stats(self.engine(), C.byref(st)))
+        ctx = self.engine()
+        capi.check(self._L.mb_stats(ctx, C.byref(st)))
         out = {}
         for name, _ in capi.MBStats._fields_:
             v = getattr(st, name)
@@ -308,11 +309,13 @@ class System:
         return out
 
     def set_profiling(self, enable: bool):
-        capi.check(self._L.mb_set_profiling(self.engine(), int(enable)))
+        ctx = self.engine()
+        capi.check(self._L.mb_set_profiling(ctx, int(enable)))
 
     def set_launch_config(self, brick_dims=(0, 0, 0), lanes_per_atom=0):
         bd = (C.c_int32 * 3)(*brick_dims)
-        capi.check(self._L.mb_set_launch_config(self.engine(), bd, lanes_per_atom))
+        ctx = self.engine()
+        capi.check(self._L.mb_set_launch_config(ctx, bd, lanes_per_atom))
 
 
 def _ptr(a):
@@ -358,7 +361,8 @@ def forces_energy(sys: System, step_n: int = 0):
 def find_neighbors(sys: System, *args, **kwargs):
     """find_neighbors(sys, nf::GPUNeighborFinder, ...) = nothing in the reference (neighbors.jl:364);
     here it forces a device rebuild and returns None."""
-    capi.check(sys._L.mb_rebuild_neighbors(sys.engine(), _ptr(sys.coords)))
+    ctx = sys.engine()
+    capi.check(sys._L.mb_rebuild_neighbors(ctx, _ptr(sys.coords)))
     return None
 
 
@@ -399,7 +403,8 @@ def simulate(sys: System, sim: VelocityVerlet, n_steps: int, init_step: int = 0,
 
 def kinetic_energy(sys: System) -> float:
     out = C.c_double(0.0)
-    capi.check(sys._L.mb_kinetic_energy(sys.engine(), _ptr(sys.velocities), C.byref(out)))
+    ctx = sys.engine()
+    capi.check(sys._L.mb_kinetic_energy(ctx, _ptr(sys.velocities), C.byref(out)))
     return out.value
 
 
@@ -410,7 +415,8 @@ def temperature(sys: System) -> float:
 
 
 def remove_CM_motion(sys: System):
-    capi.check(sys._L.mb_remove_cm_motion(sys.engine(), _ptr(sys.velocities)))
+    ctx = sys.engine()
+    capi.check(sys._L.mb_remove_cm_motion(ctx, _ptr(sys.velocities)))
     return sys
 
 

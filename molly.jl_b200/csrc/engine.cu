@@ -333,6 +333,7 @@ class Engine : public EngineBase {
                 P_.lj_cut_kind = ck;
                 P_.lj_rc = (T)rc; P_.lj_rc2 = (T)(rc * rc); P_.lj_inv_rc = (T)(1.0 / rc); P_.lj_inv_rc2 = (T)(1.0 / (rc * rc));
                 P_.lj_w14 = (T)in.weight_special;
+                P_.lj_nl = in.use_neighbors ? 1 : 0;
                 geo_sigma = (in.sigma_mix == MB_MIX_GEOMETRIC);
             } else {
                 P_.coul_kind = (in.kind == MB_COULOMB) ? COUL_PLAIN : (in.kind == MB_CRF ? COUL_CRF : COUL_EWALD);
@@ -340,6 +341,7 @@ class Engine : public EngineBase {
                 P_.c_rc = (T)rc; P_.c_rc2 = (T)(rc * rc); P_.c_inv_rc = (T)(1.0 / rc); P_.c_inv_rc2 = (T)(1.0 / (rc * rc));
                 P_.ke = (T)in.coulomb_const;
                 P_.c_w14 = (T)in.weight_special;
+                P_.c_nl = in.use_neighbors ? 1 : 0;
                 P_.alpha = (T)in.ewald_alpha;
                 if (in.kind == MB_CRF) {
                     double e = in.solvent_dielectric;
@@ -870,6 +872,7 @@ class Engine : public EngineBase {
             flag_ptr = &ctl->disp;
         } else {
             MB_TRY(sync_state_from(xc, vc));
+            skin_half2 = g_.skin_half2;  // geometry is chosen by the first build
             flag_ptr = (rebuild_every_ == 0) ? &ctl->rebuild : &ctl->disp;
         }
         auto force_eval = [&]() -> int {

@@ -58,13 +58,18 @@ __global__ void __launch_bounds__(FORCE_THREADS)
     const int sub = tid / LPA, l = tid % LPA;
     T e_acc = (T)0;
     T vir[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
-    for (int task = sub; task < hd.i_count; task += NSUB) {
+    // The trip count is CTA-uniform so that every lane reaches the shuffles below together; sub-warps
+    // past the end run with empty lists.
+    const int n_iter = (hd.i_count + NSUB - 1) / NSUB;
+    for (int it = 0; it < n_iter; it++) {
+        const int task = it * NSUB + sub;
+        const bool valid = task < hd.i_count;
         int q = 0;
         while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
         const IRow row = s_rows[q];
         const int k_in_row = task - row.cum;
-        const int slot = row.slot_begin + k_in_row;
-        const int si = row.smem_begin + k_in_row;
+        const int slot = valid ? row.slot_begin + k_in_row : 0;
+        const int si = valid ? row.smem_begin + k_in_row : 0;
         const T4 pi = s_pos[si];
         T lj_s_i = (T)0, lj_e_i = (T)0;
         if (!UNIFORM) {
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(FORCE_THREADS)
             lj_e_i = t.y;
         }
         const T kq_i = P.ke * pi.w;
-        const ushort2 cnt = counts[slot];
+        const ushort2 cnt = valid ? counts[slot] : make_ushort2(0, 0);
         T fx = (T)0, fy = (T)0, fz = (T)0;
 
         auto eval = [&](int j, auto special_tag) {
@@ -104,13 +109,19 @@ __global__ void __launch_bounds__(FORCE_THREADS)
         const int n_groups = ((int)cnt.x + 31) >> 5;
         const unsigned short* lp = list + (size_t)slot * g.stride;
         if (LPA == 8) {
+            // software pipeline: the indices of group gi+1 are in flight while group gi is evaluated
             const uint2* lp2 = reinterpret_cast<const uint2*>(lp) + l;
-            for (int gi = 0; gi < n_groups; gi++, lp2 += 8) {
-                const uint2 w = ldg_stream_u2(lp2);
+            uint2 w = make_uint2(0u, 0u);
+            if (n_groups > 0) w = ldg_stream_u2(lp2);
+            for (int gi = 0; gi < n_groups; gi++) {
+                lp2 += 8;
+                uint2 wn = w;
+                if (gi + 1 < n_groups) wn = ldg_stream_u2(lp2);
                 eval((int)(w.x & 0xffffu), std::false_type{});
                 eval((int)(w.x >> 16), std::false_type{});
                 eval((int)(w.y & 0xffffu), std::false_type{});
                 eval((int)(w.y >> 16), std::false_type{});
+                w = wn;
             }
         } else {
             // generic: logical entry m of a group lives at ((m & 7) << 2) + (m >> 3)
@@ -124,13 +135,14 @@ __global__ void __launch_bounds__(FORCE_THREADS)
         // special (1-4) pairs
         for (int m = l; m < (int)cnt.y; m += LPA) eval((int)slist[(size_t)slot * g.sstride + m], std::true_type{});
         // reduce the LPA partial forces
+        __syncwarp();
 #pragma unroll
         for (int o = LPA >> 1; o > 0; o >>= 1) {
             fx += shfl_xor(fx, o);
             fy += shfl_xor(fy, o);
             fz += shfl_xor(fz, o);
         }
-        if (l == 0) out.f4[slot] = make4<T>(fx, fy, fz, (T)0);
+        if (l == 0 && valid) out.f4[slot] = make4<T>(fx, fy, fz, (T)0);
     }
     if (ENERGY) {
         // full shell: every pair was visited from both ends -> 1/2
@@ -239,7 +251,6 @@ __global__ void __launch_bounds__(AP_THREADS)
             if (j == i) continue;
             bool excluded = false, special = false;
             for (int m = 0; m < ex_n; m++) excluded |= (ex_idx[ex_a + m] == j);
-            if (excluded) continue;
             for (int m = 0; m < sp_n; m++) special |= (sp_idx[sp_a + m] == j);
             T4 pj = s_pos[k];
             T2 lj = s_lj[k];
@@ -247,10 +258,7 @@ __global__ void __launch_bounds__(AP_THREADS)
             T dx = -mic_1d(pi.x, pj.x, Lx), dy = -mic_1d(pi.y, pj.y, Ly), dz = -mic_1d(pi.z, pj.z, Lz);
             T r2 = dx * dx + dy * dy + dz * dz;
             T fr, e;
-            if (special)
-                pair_eval<T, COUL, false, SHIFT, ENERGY, true>(P, r2, li.x, li.y, lj.x, lj.y, kq_i, pj.w, fr, e);
-            else
-                pair_eval<T, COUL, false, SHIFT, ENERGY, false>(P, r2, li.x, li.y, lj.x, lj.y, kq_i, pj.w, fr, e);
+            pair_eval_rt<T, COUL, SHIFT, ENERGY>(P, r2, li.x, li.y, lj.x, lj.y, kq_i, pj.w, excluded, special, fr, e);
             T gx = fr * dx, gy = fr * dy, gz = fr * dz;
             fx += gx; fy += gy; fz += gz;
             if (ENERGY) {

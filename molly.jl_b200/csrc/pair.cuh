@@ -33,6 +33,9 @@ struct PairParams {
     int coul_cut_kind;
     T c_rc2, c_rc, c_inv_rc, c_inv_rc2;
     T ke, krf, crf, c_w14, alpha;
+    // whether the interaction goes through the neighbour list: only then do exclusions / special flags apply
+    // (the reference's use_neighbors=false loop visits every pair with special=false, src/force.jl:828-855)
+    int lj_nl, c_nl;
 };
 
 // LJ term: returns F/r and energy for sigma^2, eps at squared distance r2 (inv_r2 = 1/r2).
@@ -139,6 +142,30 @@ __device__ __forceinline__ void pair_eval(const PairParams<T>& P, T r2, T lj_s_i
         bool in_c = r2 <= P.c_rc2;
         fr += in_c ? fc : (T)0;
         if (ENERGY) e += in_c ? ec : (T)0;
+    }
+    fr_out = fr;
+    e_out = e;
+}
+
+// Runtime-flag variant for the all-pairs kernel: exclusion and special flags per interaction.
+template <typename T, int COUL, bool SHIFT, bool ENERGY>
+__device__ __forceinline__ void pair_eval_rt(const PairParams<T>& P, T r2, T lj_s_i, T lj_e_i, T lj_s_j, T lj_e_j, T kq_i,
+                                             T q_j, bool excluded, bool special, T& fr_out, T& e_out) {
+    T inv_r = frsqrt(r2);
+    T inv_r2 = inv_r * inv_r;
+    T fr = (T)0, e = (T)0;
+    if (P.has_lj && !(excluded && P.lj_nl)) {
+        T s = P.geo_sigma ? lj_s_i * lj_s_j : lj_s_i + lj_s_j;
+        T flj, elj = (T)0;
+        lj_term<T, SHIFT, ENERGY>(P, s * s, lj_e_i * lj_e_j, r2, inv_r2, flj, elj);
+        if (special && P.lj_nl) { flj *= P.lj_w14; elj *= P.lj_w14; }
+        if (r2 <= P.lj_rc2) { fr += flj; e += elj; }
+    }
+    if (COUL != COUL_NONE && !(excluded && P.c_nl)) {
+        T fc, ec = (T)0;
+        if (special && P.c_nl) coul_term<T, COUL, SHIFT, ENERGY, true>(P, kq_i * q_j, r2, inv_r, inv_r2, fc, ec);
+        else coul_term<T, COUL, SHIFT, ENERGY, false>(P, kq_i * q_j, r2, inv_r, inv_r2, fc, ec);
+        if (r2 <= P.c_rc2) { fr += fc; e += ec; }
     }
     fr_out = fr;
     e_out = e;

@@ -205,7 +205,7 @@ static inline int FN(csr_has)(const int64_t *ptr, const int32_t *idx, int32_t i,
  * which: 0 = every interaction, 1 = only use_neighbors==0, 2 = only use_neighbors==1
  */
 static inline void FN(pair_accumulate)(const orc_system_t *s, const REAL *coords, int32_t i, int32_t j,
-                                       int special, int which, REAL *fs, double *pe_acc, double *vir) {
+                                       int special, int excluded, int which, REAL *fs, double *pe_acc, double *vir) {
     const REAL *ci = coords + 3 * (size_t)i, *cj = coords + 3 * (size_t)j;
     REAL dr[3];
     for (int d = 0; d < 3; d++) dr[d] = FN(vector_1D)(ci[d], cj[d], (REAL)s->box[d]);
@@ -221,8 +221,11 @@ static inline void FN(pair_accumulate)(const orc_system_t *s, const REAL *coords
         const orc_inter_t *in = &s->inters[k];
         if (which == 1 && in->use_neighbors) continue;
         if (which == 2 && !in->use_neighbors) continue;
+        /* eligibility / special flags only exist for interactions that go through the neighbour list
+         * (src/force.jl:828-855: the use_neighbors=false loop visits every i<j with special=false) */
+        if (in->use_neighbors && excluded) continue;
         REAL fr, pe;
-        FN(pair_eval)(in, &p, r2, special, &fr, &pe);
+        FN(pair_eval)(in, &p, r2, in->use_neighbors ? special : 0, &fr, &pe);
         frsum += fr;
         pesum += pe;
     }
@@ -241,7 +244,9 @@ static inline void FN(pair_accumulate)(const orc_system_t *s, const REAL *coords
 }
 
 /*
- * Brute-force O(N^2) evaluation over all i<j pairs that are not excluded.
+ * Brute-force O(N^2) evaluation over all i<j pairs. Interactions with
+ * use_neighbors=true skip excluded pairs and see the special flag; interactions
+ * with use_neighbors=false see every pair with special=false (src/force.jl:828-855).
  * This is the semantic definition of the path:
  * the neighbour structures only pre-filter. Threads own private force copies
  * that are reduced at the end (src/force.jl:886-969, :808-826).
@@ -271,9 +276,9 @@ int FN(orc_forces_allpairs)(const orc_system_t *s, const void *coords_v, void *f
 #pragma omp for schedule(dynamic, 16)
         for (int64_t i = 0; i < n; i++) {
             for (int64_t j = i + 1; j < n; j++) {
-                if (FN(csr_has)(s->excl_ptr, s->excl_idx, (int32_t)i, (int32_t)j)) continue;
+                int excluded = FN(csr_has)(s->excl_ptr, s->excl_idx, (int32_t)i, (int32_t)j);
                 int special = FN(csr_has)(s->spec_ptr, s->spec_idx, (int32_t)i, (int32_t)j);
-                FN(pair_accumulate)(s, coords, (int32_t)i, (int32_t)j, special, 0, myfs,
+                FN(pair_accumulate)(s, coords, (int32_t)i, (int32_t)j, special, excluded, 0, myfs,
                                     pe_out ? &mype : NULL, virial_out ? myvir : NULL);
             }
         }
@@ -429,7 +434,7 @@ int FN(orc_forces_nl)(const orc_system_t *s, const void *coords_v, const orc_nl_
 #pragma omp for schedule(dynamic, 16)
             for (int64_t i = 0; i < n; i++)
                 for (int64_t j = i + 1; j < n; j++)
-                    FN(pair_accumulate)(s, coords, (int32_t)i, (int32_t)j, 0, 1, myfs, pe_out ? &mype : NULL,
+                    FN(pair_accumulate)(s, coords, (int32_t)i, (int32_t)j, 0, 0, 1, myfs, pe_out ? &mype : NULL,
                                         virial_out ? myvir : NULL);
         }
         if (any_nl) {
@@ -437,7 +442,7 @@ int FN(orc_forces_nl)(const orc_system_t *s, const void *coords_v, const orc_nl_
             for (int64_t b = 0; b < n_blocks; b++) {
                 int64_t lo = b * 512, hi = lo + 512 < n_list ? lo + 512 : n_list;
                 for (int64_t k = lo; k < hi; k++)
-                    FN(pair_accumulate)(s, coords, list[k].i, list[k].j, list[k].special, 2, myfs,
+                    FN(pair_accumulate)(s, coords, list[k].i, list[k].j, list[k].special, 0, 2, myfs,
                                         pe_out ? &mype : NULL, virial_out ? myvir : NULL);
             }
         }

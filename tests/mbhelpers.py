@@ -57,7 +57,7 @@ def readme_system(n: int = 100, box: float = 2.0, seed: int = 1, min_dist: float
                 mass=np.full(n, 10.0), charge=np.zeros(n), sigma=np.full(n, 0.3), eps=np.full(n, 0.2))
 
 
-def molecular_system(n_mol: int, box, seed: int = 7, dtype=np.float64):
+def molecular_system(n_mol: int, box, seed: int = 7, dtype=np.float64, stable: bool = False):
     """Small charged 4-site chain molecules A-B-C-D on a jittered grid: 1-2 and 1-3 pairs excluded,
     1-4 pairs special; three LJ types including a zero-epsilon one (TIP3P-hydrogen-like)."""
     rng = np.random.default_rng(seed)
@@ -71,6 +71,11 @@ def molecular_system(n_mol: int, box, seed: int = 7, dtype=np.float64):
     ts = [0.32, 0.30, 0.25, 0.10]
     te = [0.6, 0.4, 0.2, 0.0]
     tm = [12.0, 14.0, 16.0, 1.008]
+    if stable:  # for dynamics without bonded terms: every site keeps a repulsive core, charges are mild
+        te = [0.6, 0.4, 0.2, 0.15]
+        ts = [0.32, 0.30, 0.25, 0.22]
+        tq = [0.2, -0.2, 0.15, -0.15]
+        tm = [12.0, 14.0, 16.0, 4.0]
     for m, c in enumerate(centers):
         d = rng.normal(size=3)
         d /= np.linalg.norm(d)

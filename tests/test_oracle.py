@@ -58,7 +58,7 @@ def test_mixing_rules():
 
 def test_crf_behaviour():
     # test/interactions.jl:506-660: zero beyond cutoff; special pairs = weighted plain Coulomb
-    crf = o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=0.5)
+    crf = o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=0.5, use_neighbors=True)
     f, e = _pair(crf, 1.2, q=1.0)
     assert f == 0.0 and e == 0.0
     s = o.OracleSystem(box=[5.0] * 3, mass=[1, 1], charge=[1.0, 1.0], sigma=[0, 0], eps=[0, 0], inters=[crf],
