@@ -80,6 +80,9 @@ typedef struct {
      * mb_set_profiling(ctx, 1) is active: force kernel, VelocityVerlet kernels, rebuild pipeline */
     double force_ms, vv_ms, rebuild_ms;
     int64_t force_launches, vv_launches, rebuild_launches;
+    int32_t graph_mode;        /* last mb_simulate_vv: 1 = CUDA-graph step with conditional rebuild node,
+                                * 0 = stream launches, -1 = graph construction failed (stream launches) */
+    int32_t reserved_;
 } mb_stats_t;
 
 const char* mb_last_error(void);

@@ -30,7 +30,10 @@ struct Control {
     int max_halo;
     int max_special;
     unsigned int ticket;  // last-block-done counter
-    int pad[2];
+    int rebuild_every;    // fixed-interval policy (0 = displacement-triggered)
+    long long step;       // MD step counter (simulate!'s step_n), advanced on the device
+    long long init_step;  // step_n at the start of the current mb_simulate_vv call
+    unsigned int rng[4];  // Andersen thermostat: ctr1 lo/hi, key lo/hi
 };
 
 struct BrickHdr {

@@ -150,9 +150,20 @@ class Engine : public EngineBase {
         sm_count_ = prop.multiProcessorCount;
         smem_optin_ = prop.sharedMemPerBlockOptin;
         for (int d = 0; d < 3; d++) box_[d] = 0;
-        prof_.stream = stream;
+        if (!stream_) {
+            // a real (blocking) stream: graph capture is not allowed on the legacy default stream, and a blocking
+            // stream keeps the implicit ordering with work the caller issues on the default stream
+            if (cudaStreamCreateWithFlags(&stream_, cudaStreamDefault) == cudaSuccess) own_stream_ = true;
+            else stream_ = nullptr;
+        }
+        prof_.stream = stream_;
+        const char* ng = getenv("MOLLYB200_NO_GRAPH");
+        graph_enabled_ = !(ng && ng[0] == '1');
     }
-    ~Engine() override {}
+    ~Engine() override {
+        destroy_graph();
+        if (own_stream_) cudaStreamDestroy(stream_);
+    }
 
     // ------------------------------------------------------------------------------------------
     int set_atoms_aos(int64_t n, const void* aos) override {
@@ -468,11 +479,14 @@ class Engine : public EngineBase {
                         double halo = (bx + 4.0) * (by + 4.0) * (bz + 4.0) * rho_c * 1.25 + 64;
                         double smem = halo * bytes_per_atom;
                         if (smem > smem_budget || halo > 60000) continue;
-                        double occ = std::floor(smem_budget / smem);
+                        double occ = std::min(8.0, std::floor(smem_budget / smem));
+                        // latency hiding improves with resident CTAs (8 warps each): measured shape, saturating at ~6
+                        static const double eff_tab[9] = {0.0, 0.35, 0.55, 0.70, 0.80, 0.88, 0.95, 0.97, 1.0};
+                        double eff = eff_tab[(int)occ];
                         double owned = (double)bx * by * bz * rho_c;
-                        double cost_b = owned * nbrs + 0.5 * halo;
+                        double cost_b = owned * nbrs + 2.0 * halo;
                         double nbr = std::ceil((double)g.nc[0] / bx) * std::ceil((double)g.nc[1] / by) * std::ceil((double)g.nc[2] / bz);
-                        double t = std::ceil(nbr / sm_count_) * cost_b * (occ < 2 ? 1.3 : 1.0);
+                        double t = std::ceil(nbr / sm_count_) * cost_b / eff;
                         if (t < best_t * 0.999) { best_t = t; best[0] = bx; best[1] = by; best[2] = bz; }
                     }
         }
@@ -639,6 +653,7 @@ class Engine : public EngineBase {
             if (c.overflow) return set_error(MB_ERR_CAPACITY, "neighbour capacity overflow during first build");
             last_ctl_ = c;
             have_list_ = true;
+            geom_version_++;
             return MB_OK;
         }
         return set_error(MB_ERR_CAPACITY, "could not find a brick size that fits in shared memory");
@@ -833,6 +848,128 @@ class Engine : public EngineBase {
     }
 
     // ------------------------------------------------------------------------------------------
+    // One MD step enqueued on the stream. In capture mode the neighbour rebuild becomes the body of a CUDA-graph
+    // conditional node driven by decide_kernel, otherwise the gated pipeline is enqueued when it may be needed.
+    struct StepCfg {
+        T dt, dt_half, skin_half2, kT;
+        double prob, inv_mass;
+        int do_cm;        // 0/1 constant, or -1: caller decides per step (stream path only)
+        bool thermostat;
+        int* flag_ptr;
+    };
+    int enqueue_step(const StepCfg& c, int do_cm_now, bool clear_cm_after_k1, bool capture,
+                     cudaGraphConditionalHandle handle, cudaGraph_t graph, cudaGraph_t* body_out, bool host_rebuild_hint) {
+        const int nb = (int)((n_ + 255) / 256);
+        const int vvb = (int)((n_ + VV_THREADS - 1) / VV_THREADS);
+        Control* ctl = d_ctl_.as<Control>();
+        CmState<T>* cm = d_cm_.as<CmState<T>>();
+        prof_.begin(Prof::VV);
+        vv_kick_drift_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(),
+                                                         d_pos4_.as<T4>(), d_vel4_.as<T4>(), c.flag_ptr);
+        prof_.end(Prof::VV);
+        launches_++;
+        if (clear_cm_after_k1) {
+            clear_cm_kernel<T><<<1, 1, 0, stream_>>>(cm);
+            launches_++;
+        }
+        decide_kernel<<<1, 32, 0, stream_>>>(ctl, handle, capture && path_ == 1 ? 1 : 0);
+        launches_++;
+        if (path_ == 0) {
+            wrap_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_ap_, d_pos4_.as<T4>());
+            launches_++;
+        } else if (capture) {
+            // splice a conditional IF node into the capture; its body is filled in by the caller
+            cudaStreamCaptureStatus status;
+            const cudaGraphNode_t* deps = nullptr;
+            size_t ndeps = 0;
+            cudaGraph_t gcap = nullptr;
+            MB_CUDA(cudaStreamGetCaptureInfo_v2(stream_, &status, nullptr, &gcap, &deps, &ndeps));
+            cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+            cp.type = cudaGraphNodeTypeConditional;
+            cp.conditional.handle = handle;
+            cp.conditional.type = cudaGraphCondTypeIf;
+            cp.conditional.size = 1;
+            cudaGraphNode_t cnode;
+            MB_CUDA(cudaGraphAddNode(&cnode, graph, deps, ndeps, &cp));
+            *body_out = cp.conditional.phGraph_out[0];
+            MB_CUDA(cudaStreamUpdateCaptureDependencies(stream_, &cnode, 1, cudaStreamSetCaptureDependencies));
+        } else {
+            if (rebuild_every_ == 0 || host_rebuild_hint) MB_TRY(enqueue_rebuild(true, false));
+        }
+        if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
+        else MB_TRY(launch_force(false));
+        prof_.begin(Prof::VV);
+        vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>((int)n_, c.dt_half, do_cm_now, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
+                                                            d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0);
+        prof_.end(Prof::VV);
+        launches_++;
+        if (c.thermostat) {
+            andersen_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, c.kT, c.prob, d_orig_.as<int>(), d_mass_.as<T>(), d_vel4_.as<T4>(), cm, ctl);
+            launches_++;
+        }
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
+
+    struct GraphKey {
+        int path, do_cm, thermostat, geom_version, rebuild_every;
+        double dt, kT, prob;
+        int64_t n;
+        bool operator==(const GraphKey& o) const {
+            return path == o.path && do_cm == o.do_cm && thermostat == o.thermostat && geom_version == o.geom_version &&
+                   rebuild_every == o.rebuild_every && dt == o.dt && kT == o.kT && prob == o.prob && n == o.n;
+        }
+    };
+    void destroy_graph() {
+        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        if (graph_) cudaGraphDestroy(graph_);
+        graph_exec_ = nullptr;
+        graph_ = nullptr;
+    }
+    // Capture one MD step (K1, decide, [IF rebuild], force, K2, [thermostat]) into an executable graph.
+    int build_step_graph(const StepCfg& c, const GraphKey& key) {
+        destroy_graph();
+        const bool prof_was = prof_.enabled;
+        prof_.enabled = false;
+        const int64_t launches_before = launches_;
+        auto fail = [&](int rc) {
+            cudaStreamCaptureStatus st;
+            if (cudaStreamIsCapturing(stream_, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+                cudaGraph_t junk = nullptr;
+                cudaStreamEndCapture(stream_, &junk);
+            }
+            cudaGetLastError();
+            destroy_graph();
+            prof_.enabled = prof_was;
+            launches_ = launches_before;
+            return rc;
+        };
+        if (cudaGraphCreate(&graph_, 0) != cudaSuccess) return fail(MB_ERR_CUDA);
+        cudaGraphConditionalHandle handle = 0;
+        if (path_ == 1 && cudaGraphConditionalHandleCreate(&handle, graph_, 0, cudaGraphCondAssignDefault) != cudaSuccess)
+            return fail(MB_ERR_CUDA);
+        if (cudaStreamBeginCaptureToGraph(stream_, graph_, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+            return fail(MB_ERR_CUDA);
+        cudaGraph_t body = nullptr;
+        if (enqueue_step(c, c.do_cm, false, true, handle, graph_, &body, false) != MB_OK) return fail(MB_ERR_CUDA);
+        cudaGraph_t out = nullptr;
+        if (cudaStreamEndCapture(stream_, &out) != cudaSuccess) return fail(MB_ERR_CUDA);
+        const int64_t step_nodes = launches_ - launches_before;
+        if (path_ == 1) {
+            if (!body) return fail(MB_ERR_CUDA);
+            if (cudaStreamBeginCaptureToGraph(stream_, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+                return fail(MB_ERR_CUDA);
+            if (enqueue_rebuild(true, false) != MB_OK) return fail(MB_ERR_CUDA);
+            if (cudaStreamEndCapture(stream_, &out) != cudaSuccess) return fail(MB_ERR_CUDA);
+        }
+        if (cudaGraphInstantiate(&graph_exec_, graph_, 0) != cudaSuccess) return fail(MB_ERR_CUDA);
+        prof_.enabled = prof_was;
+        launches_ = launches_before;
+        graph_step_launches_ = step_nodes;
+        graph_key_ = key;
+        return MB_OK;
+    }
+
     int simulate_vv(void* coords, void* vels, const mb_vv_params_t* p) override {
         MB_TRY(prepare());
         if (!coords || !vels || !p) return set_error(MB_ERR_INVALID, "null argument");
@@ -846,13 +983,16 @@ class Engine : public EngineBase {
         const int vvb = (int)((n_ + VV_THREADS - 1) / VV_THREADS);
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
-        const T dt = (T)p->dt, dt_half = (T)p->dt / (T)2;
-        const double inv_mass = (total_mass_ > 0) ? 1.0 / total_mass_ : 0.0;
         clear_cm_kernel<T><<<1, 1, 0, stream_>>>(cm);
         launches_++;
-        const bool thermostat = p->andersen_kT > 0 && p->andersen_prob > 0;
-        T skin_half2 = g_.skin_half2;
-        int* flag_ptr = nullptr;
+        StepCfg c;
+        c.dt = (T)p->dt;
+        c.dt_half = (T)p->dt / (T)2;
+        c.inv_mass = (total_mass_ > 0) ? 1.0 / total_mass_ : 0.0;
+        c.thermostat = p->andersen_kT > 0 && p->andersen_prob > 0;
+        c.kT = (T)p->andersen_kT;
+        c.prob = p->andersen_prob;
+        c.do_cm = (p->remove_cm_every == 0) ? 0 : (p->remove_cm_every == 1 ? 1 : -1);
         if (path_ == 0) {
             init_slots_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, xc, d_charge_in_.as<T>(), d_ljp_in_.as<T2>(), d_mass_in_.as<T>(),
                                                           d_pos4_.as<T4>(), d_vel4_.as<T4>(), d_lj2_.as<T2>(), d_orig_.as<int>(),
@@ -868,62 +1008,65 @@ class Engine : public EngineBase {
                                                       d_vel4_.as<T4>(), &ctl->disp);
             wrap_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g0, d_pos4_.as<T4>());
             launches_ += 2;
-            skin_half2 = std::numeric_limits<T>::infinity();
-            flag_ptr = &ctl->disp;
+            c.skin_half2 = std::numeric_limits<T>::infinity();
+            c.flag_ptr = &ctl->disp;
         } else {
             MB_TRY(sync_state_from(xc, vc));
-            skin_half2 = g_.skin_half2;  // geometry is chosen by the first build
-            flag_ptr = (rebuild_every_ == 0) ? &ctl->rebuild : &ctl->disp;
+            c.skin_half2 = g_.skin_half2;  // geometry is chosen by the first build
+            c.flag_ptr = (rebuild_every_ == 0) ? &ctl->rebuild : &ctl->disp;
         }
-        auto force_eval = [&]() -> int {
-            if (path_ == 0) return launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>());
-            return launch_force(false);
-        };
+        // step bookkeeping lives on the device (tail of Control)
+        {
+            struct Tail { int rebuild_every; long long step, init_step; unsigned int rng[4]; } t;
+            static_assert(sizeof(Tail) == sizeof(Control) - offsetof(Control, rebuild_every), "Control tail layout");
+            t.rebuild_every = rebuild_every_;
+            t.step = p->init_step;
+            t.init_step = p->init_step;
+            t.rng[0] = (unsigned int)p->rng_ctr1; t.rng[1] = (unsigned int)(p->rng_ctr1 >> 32);
+            t.rng[2] = (unsigned int)p->rng_key; t.rng[3] = (unsigned int)(p->rng_key >> 32);
+            MB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(ctl) + offsetof(Control, rebuild_every), &t, sizeof(t),
+                                    cudaMemcpyHostToDevice, stream_));
+            MB_CUDA(cudaStreamSynchronize(stream_));  // t is a local
+        }
         bool cm_pending = false;  // host mirror of cm->valid
         if (p->init_step == 0 && p->remove_cm_every != 0) {
             // remove_CM_motion! before the first force evaluation (simulators.jl:563): zero-length kick
-            vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>((int)n_, (T)0, 1, inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
+            vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>((int)n_, (T)0, 1, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
                                                                 d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0);
             launches_++;
             cm_pending = true;
         }
-        MB_TRY(force_eval());
-        for (int64_t k = 1; k <= p->n_steps; k++) {
-            const int64_t step_n = p->init_step + k;
-            prof_.begin(Prof::VV);
-            vv_kick_drift_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, dt, dt_half, skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(),
-                                                             d_pos4_.as<T4>(), d_vel4_.as<T4>(), flag_ptr);
-            prof_.end(Prof::VV);
-            launches_++;
-            const int do_cm = (p->remove_cm_every != 0 && step_n % p->remove_cm_every == 0) ? 1 : 0;
-            if (cm_pending && !do_cm) {  // K1 consumed v_cm; nothing will overwrite it this step
-                clear_cm_kernel<T><<<1, 1, 0, stream_>>>(cm);
-                launches_++;
+        if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
+        else MB_TRY(launch_force(false));
+
+        // CUDA-graph path: static per-step sequence (remove_CM_motion in {0,1}, no stage timers requested)
+        bool use_graph = graph_enabled_ && !graph_failed_ && !prof_.enabled && c.do_cm >= 0 && p->n_steps >= 4 &&
+                         !(cm_pending && c.do_cm == 0);
+        if (use_graph) {
+            GraphKey key{path_, c.do_cm, c.thermostat ? 1 : 0, geom_version_, rebuild_every_, p->dt, p->andersen_kT, p->andersen_prob, n_};
+            if (!graph_exec_ || !(key == graph_key_)) {
+                if (build_step_graph(c, key) != MB_OK) {
+                    graph_failed_ = true;  // stay on the stream path for this context
+                    use_graph = false;
+                }
             }
-            cm_pending = false;
-            if (path_ == 0) {
-                wrap_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_ap_, d_pos4_.as<T4>());
-                launches_++;
-            } else {
-                if (rebuild_every_ > 0 && k > 1 && (step_n - 1) % rebuild_every_ == 0) MB_TRY(set_flag_rebuild());
-                if (rebuild_every_ == 0 || (k > 1 && (step_n - 1) % rebuild_every_ == 0)) MB_TRY(enqueue_rebuild(true, false));
+        }
+        graph_used_ = use_graph;
+        if (use_graph) {
+            for (int64_t k = 1; k <= p->n_steps; k++) MB_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+            launches_ += graph_step_launches_ * p->n_steps;  // rebuild-body kernels are not counted
+            n_force_evals_ += p->n_steps;
+            n_steps_ += p->n_steps;
+        } else {
+            for (int64_t k = 1; k <= p->n_steps; k++) {
+                const int64_t step_n = p->init_step + k;
+                const int do_cm = (p->remove_cm_every != 0 && step_n % p->remove_cm_every == 0) ? 1 : 0;
+                const bool clear_after_k1 = cm_pending && !do_cm;  // K1 consumed v_cm; nothing overwrites it this step
+                const bool hint = rebuild_every_ > 0 && k > 1 && (step_n - 1) % rebuild_every_ == 0;
+                MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint));
+                cm_pending = (do_cm != 0) && !c.thermostat;
+                n_steps_++;
             }
-            MB_TRY(force_eval());
-            prof_.begin(Prof::VV);
-            vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>((int)n_, dt_half, do_cm, inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
-                                                                d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0);
-            prof_.end(Prof::VV);
-            launches_++;
-            cm_pending = do_cm != 0;
-            if (thermostat) {
-                andersen_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, (T)p->andersen_kT, p->andersen_prob, (uint32_t)p->rng_ctr1,
-                                                            (uint32_t)(p->rng_ctr1 >> 32), (uint32_t)p->rng_key,
-                                                            (uint32_t)(p->rng_key >> 32), (uint32_t)step_n, d_orig_.as<int>(),
-                                                            d_mass_.as<T>(), d_vel4_.as<T4>(), cm, ctl);
-                launches_++;
-                cm_pending = false;
-            }
-            n_steps_++;
         }
         // export
         T* xo = c_dev ? reinterpret_cast<T*>(coords) : d_stage_a_.as<T>();
@@ -998,6 +1141,7 @@ class Engine : public EngineBase {
         o->path = path_;
         o->r_list = r_list_;
         o->kernel_launches = launches_;
+        o->graph_mode = graph_used_ ? 1 : (graph_failed_ ? -1 : 0);
         prof_.collect();
         o->force_ms = prof_.ms[Prof::FORCE]; o->force_launches = prof_.count[Prof::FORCE];
         o->vv_ms = prof_.ms[Prof::VV]; o->vv_launches = prof_.count[Prof::VV];
@@ -1041,8 +1185,13 @@ class Engine : public EngineBase {
     PairParams<T> P_;
     Geom<T> g_, g_ap_;
     Control last_ctl_;
-    int64_t launches_ = 0, n_force_evals_ = 0, n_steps_ = 0;
+    int64_t launches_ = 0, n_force_evals_ = 0, n_steps_ = 0, graph_step_launches_ = 0;
     Prof prof_;
+    cudaGraph_t graph_ = nullptr;
+    cudaGraphExec_t graph_exec_ = nullptr;
+    GraphKey graph_key_;
+    bool graph_enabled_ = true, graph_failed_ = false, graph_used_ = false, own_stream_ = false;
+    int geom_version_ = 0;
     DevBuf d_mass_in_, d_charge_in_, d_ljp_in_;
     DevBuf d_pos4_, d_vel4_, d_f4_, d_xref4_, d_lj2_, d_orig_, d_inv_orig_, d_mass_;
     DevBuf d_pos4_t_, d_vel4_t_, d_lj2_t_, d_orig_t_, d_mass_t_;

@@ -149,6 +149,17 @@ __global__ void vv_kick_drift_kernel(int n, T dt, T dt_half, T skin_half2, const
     if (dx * dx + dy * dy + dz * dz > skin_half2) *flag = 1;
 }
 
+// ---- step bookkeeping on the device: advance step_n, apply the fixed-interval neighbour policy
+// (find_neighbors every n_steps, src/neighbors.jl:671) and publish the rebuild decision to the CUDA
+// graph's conditional node (when the step runs as a graph).
+__global__ void decide_kernel(Control* ctl, cudaGraphConditionalHandle handle, int use_handle) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long step_n = ++ctl->step;
+    const long long k = step_n - ctl->init_step;
+    if (ctl->rebuild_every > 0 && k > 1 && (step_n - 1) % ctl->rebuild_every == 0) ctl->rebuild = 1;
+    if (use_handle) cudaGraphSetConditional(handle, ctl->rebuild ? 1u : 0u);
+}
+
 // ---- K2: second half kick + centre-of-mass momentum -------------------------------------------
 // Every CTA writes its partial sum(m v); the last CTA to finish adds the partials in index order
 // (deterministic) and publishes v_cm = sum(m v) / sum(m) (src/spatial.jl:901-916). The subtraction is
@@ -235,11 +246,12 @@ __global__ void clear_cm_kernel(CmState<T>* cm) {
 // order; normals by Box-Muller. Statistical parity only (the reference's normal transform lives in
 // the un-vendored PhiloxRNG.jl). Consumes the pending v_cm.
 template <typename T>
-__global__ void andersen_kernel(int n, T kT, double prob, uint32_t ctr1_lo, uint32_t ctr1_hi, uint32_t key_lo,
-                                uint32_t key_hi, uint32_t step_lo, const int* __restrict__ orig,
+__global__ void andersen_kernel(int n, T kT, double prob, const int* __restrict__ orig,
                                 const T* __restrict__ mass, typename VT<T>::T4* __restrict__ vel4,
                                 CmState<T>* __restrict__ cm, Control* __restrict__ ctl) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ctr1_lo = ctl->rng[0], ctr1_hi = ctl->rng[1], key_lo = ctl->rng[2], key_hi = ctl->rng[3];
+    const uint32_t step_lo = (uint32_t)ctl->step;
     if (s < n) {
         typename VT<T>::T4 v = vel4[s];
         if (cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
