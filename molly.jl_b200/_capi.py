@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmollyb200.so")
+LIB_PATH = os.environ.get("MOLLYB200_LIB") or os.path.join(_HERE, "libmollyb200.so")  # override: tuning variants
 
 MB_LJ, MB_COULOMB, MB_CRF, MB_EWALD_REAL = 0, 1, 2, 3
 MB_CUT_NONE, MB_CUT_DISTANCE, MB_CUT_SHIFTED_POTENTIAL, MB_CUT_SHIFTED_FORCE = 0, 1, 2, 3

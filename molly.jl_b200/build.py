@@ -30,8 +30,9 @@ def needs_build() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """defines/out: build a tuning variant (e.g. defines=("MB_LIST_BATCH=4",), out="libmollyb200_b4.so")."""
+    if out is None and not force and not needs_build():
         return LIB
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [
@@ -40,16 +41,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-ccbin", host_cxx,
         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
         "--expt-relaxed-constexpr",
-        "-shared", "-o", LIB,
+        "-shared", "-o", os.path.join(HERE, out) if out else LIB,
     ]
+    cmd += [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-lcudart"]
     print("[mollyb200] " + " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
-    return LIB
+    return os.path.join(HERE, out) if out else LIB
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None)

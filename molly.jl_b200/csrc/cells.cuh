@@ -390,14 +390,15 @@ __device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickH
     double org[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) org[d] = (double)(B[d] * g.b[d]) * g.celld[d];
-    const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    for (int r = wid; r < g.max_runs; r += nw) {
+    // 8-lane groups, one run each (a run is ~40 atoms): four runs per warp instruction
+    const int l8 = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
+    for (int r = grp; r < g.max_runs; r += ngrp) {
         Run run = my_runs[r];
         if (run.count <= 0) continue;
-        double ox = (double)((run.shift & 3) - 1) * g.Ld[0] - org[0];
-        double oy = (double)(((run.shift >> 2) & 3) - 1) * g.Ld[1] - org[1];
-        double oz = (double)(((run.shift >> 4) & 3) - 1) * g.Ld[2] - org[2];
-        for (int k = lane; k < run.count; k += 32) {
+        const double ox = (double)((run.shift & 3) - 1) * g.Ld[0] - org[0];
+        const double oy = (double)(((run.shift >> 2) & 3) - 1) * g.Ld[1] - org[1];
+        const double oz = (double)(((run.shift >> 4) & 3) - 1) * g.Ld[2] - org[2];
+        for (int k = l8; k < run.count; k += 8) {
             T4 p = s_pos[run.soff + k];
             p.x = (T)((double)p.x + ox);
             p.y = (T)((double)p.y + oy);
@@ -412,7 +413,7 @@ __device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickH
 // One CTA per brick, one warp per owned atom. Entries are 16-bit halo indices written in the lane-
 // swizzled order the force kernel reads (see force.cuh). Excluded pairs are dropped here; special
 // (1-4) pairs go to a separate short list.
-template <typename T, bool COUNT_ONLY>
+template <typename T, bool COUNT_ONLY, bool HAS_EX>
 __global__ void __launch_bounds__(256)
     build_lists_kernel(Control* __restrict__ ctl, Geom<T> g, const BrickHdr* __restrict__ hdrs,
                        const Run* __restrict__ runs, const IRow* __restrict__ irows, const ushort2* __restrict__ hcs,
@@ -476,11 +477,27 @@ __global__ void __launch_bounds__(256)
         int count = 0, scount = 0;
         unsigned short* my_list = list + (size_t)slot * g.stride;
         unsigned short* my_slist = slist + (size_t)slot * g.sstride;
+        // Only the part of each halo row that can hold a neighbour is scanned: with dy, dz the distance from the
+        // atom to the row's (y,z) cell slab, candidates need |dx| <= sqrt(r_list^2 - dy^2 - dz^2).
+        const T cyv = (T)g.celld[1], czv = (T)g.celld[2];
+        const T inv_cx = g.inv_cell[0];
+        const T rl2 = g.rlist2 * (T)1.0001;
         for (int rz = iz; rz <= iz + 2 * g.h; rz++) {
+            const T zlo = (T)(rz - g.h) * czv;
+            const T dzm = fmax(fmax(zlo - pi.z, pi.z - (zlo + czv)), (T)0);
             for (int ry = iy; ry <= iy + 2 * g.h; ry++) {
+                const T ylo = (T)(ry - g.h) * cyv;
+                const T dym = fmax(fmax(ylo - pi.y, pi.y - (ylo + cyv)), (T)0);
+                const T rem = rl2 - dym * dym - dzm * dzm;
+                if (rem < (T)0) continue;
+                const T wx = fsqrt(rem) + (T)1e-4;
+                int rx_lo = (int)ffloor((pi.x - wx) * inv_cx) + g.h;
+                int rx_hi = (int)ffloor((pi.x + wx) * inv_cx) + g.h;
+                rx_lo = max(rx_lo, ix);
+                rx_hi = min(rx_hi, ix + 2 * g.h);
                 int hcrow = (rz * g.H[1] + ry) * g.H[0];
-                int a = s_hcs[hcrow + ix].x;
-                int e = s_hcs[hcrow + ix + 2 * g.h].y;
+                int a = s_hcs[hcrow + rx_lo].x;
+                int e = s_hcs[hcrow + rx_hi].y;
                 for (int cbase = a; cbase < e; cbase += 32) {
                     int c = cbase + lane;
                     bool in = false, special = false;
@@ -490,9 +507,9 @@ __global__ void __launch_bounds__(256)
                         T d2 = dx * dx + dy * dy + dz * dz;
                         in = d2 <= g.rlist2;
                     }
-                    int oj = in ? s_orig[c] : -1;
+                    int oj = (HAS_EX && in) ? s_orig[c] : -1;
                     // exclusions (warp-uniform loops over the partner lists)
-                    if (ex_n > 0) {
+                    if (HAS_EX && ex_n > 0) {
                         int nn = min(ex_n, 32);
                         for (int k = 0; k < nn; k++) {
                             int v = __shfl_sync(0xffffffffu, my_ex, k);
@@ -501,7 +518,7 @@ __global__ void __launch_bounds__(256)
                         for (int k = 32; k < ex_n; k++)
                             if (ex_idx[ex_a + k] == oj) in = false;
                     }
-                    if (sp_n > 0) {
+                    if (HAS_EX && sp_n > 0) {
                         int nn = min(sp_n, 32);
                         for (int k = 0; k < nn; k++) {
                             int v = __shfl_sync(0xffffffffu, my_sp, k);

@@ -380,6 +380,9 @@ class Engine : public EngineBase {
         if (P_.uniform_lj) {
             P_.uni_sig2 = P_.has_lj ? h_sigma_[0] * h_sigma_[0] : (T)0;
             P_.uni_eps = P_.has_lj ? h_eps_[0] : (T)0;
+            const double s6 = std::pow((double)h_sigma_[0], 6.0), e0 = P_.has_lj ? (double)h_eps_[0] : 0.0;
+            P_.uni_A = (T)(48.0 * e0 * s6 * s6);
+            P_.uni_B = (T)(24.0 * e0 * s6);
         }
         total_mass_ = 0;
         for (int64_t i = 0; i < n_; i++) total_mass_ += (double)h_mass_[i];
@@ -531,6 +534,27 @@ class Engine : public EngineBase {
         return MB_OK;
     }
 
+    // launch the list builder (count-only or real; with or without exclusion handling)
+    int launch_build(bool count_only) {
+        const size_t smem = build_smem_bytes();
+        const bool has_ex = !ex_ptr_.empty() || !sp_ptr_.empty();
+        auto go = [&](auto kern) -> int {
+            MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<g_.nbricks, 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
+                                                     d_irows_.as<IRow>(), d_hcs_.as<ushort2>(), d_pos4_.as<T4>(), d_orig_.as<int>(),
+                                                     ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(),
+                                                     count_only ? nullptr : d_list_.as<unsigned short>(),
+                                                     count_only ? nullptr : d_slist_.as<unsigned short>(),
+                                                     count_only ? nullptr : d_counts_.as<ushort2>());
+            return MB_OK;
+        };
+        if (count_only) { if (has_ex) MB_TRY(go(build_lists_kernel<T, true, true>)); else MB_TRY(go(build_lists_kernel<T, true, false>)); }
+        else { if (has_ex) MB_TRY(go(build_lists_kernel<T, false, true>)); else MB_TRY(go(build_lists_kernel<T, false, false>)); }
+        launches_++;
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
+
     // enqueue the gated rebuild sequence. count_only: first pass of the capacity derivation.
     int enqueue_rebuild(bool lists, bool count_only) {
         const Geom<T>& g = g_;
@@ -557,23 +581,7 @@ class Engine : public EngineBase {
             ctl, g, d_cell_start_.as<int>(), d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(),
             d_hcs_.as<ushort2>(), P_.uniform_lj);
         launches_ += 8;
-        if (lists) {
-            const size_t smem = build_smem_bytes();
-            if (count_only) {
-                MB_CUDA(cudaFuncSetAttribute(build_lists_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                build_lists_kernel<T, true><<<g.nbricks, 256, smem, stream_>>>(
-                    ctl, g, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(), d_hcs_.as<ushort2>(),
-                    d_pos4_.as<T4>(), d_orig_.as<int>(), ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(), nullptr,
-                    nullptr, nullptr);
-            } else {
-                MB_CUDA(cudaFuncSetAttribute(build_lists_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                build_lists_kernel<T, false><<<g.nbricks, 256, smem, stream_>>>(
-                    ctl, g, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(), d_hcs_.as<ushort2>(),
-                    d_pos4_.as<T4>(), d_orig_.as<int>(), ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(),
-                    d_list_.as<unsigned short>(), d_slist_.as<unsigned short>(), d_counts_.as<ushort2>());
-            }
-            launches_ += 1;
-        }
+        if (lists) MB_TRY(launch_build(count_only));
         if (!count_only) {
             rebuild_finish_kernel<<<1, 32, 0, stream_>>>(ctl);
             launches_ += 1;
@@ -630,16 +638,7 @@ class Engine : public EngineBase {
                 continue;
             }
             // pass B: count neighbours (flag still set because finish did not run)
-            {
-                const size_t smem = build_smem_bytes();
-                MB_CUDA(cudaFuncSetAttribute(build_lists_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                build_lists_kernel<T, true><<<g_.nbricks, 256, smem, stream_>>>(
-                    d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(), d_hcs_.as<ushort2>(),
-                    d_pos4_.as<T4>(), d_orig_.as<int>(), ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(), nullptr, nullptr,
-                    nullptr);
-                launches_++;
-                MB_CUDA(cudaGetLastError());
-            }
+            MB_TRY(launch_build(true));
             MB_TRY(read_ctl(c));
             int stride = (int)(c.max_neighbors * (1.0 + 0.10 * cap_scale_)) + 16;
             stride = (stride + 31) & ~31;
@@ -860,7 +859,7 @@ class Engine : public EngineBase {
     int enqueue_step(const StepCfg& c, int do_cm_now, bool clear_cm_after_k1, bool capture,
                      cudaGraphConditionalHandle handle, cudaGraph_t graph, cudaGraph_t* body_out, bool host_rebuild_hint) {
         const int nb = (int)((n_ + 255) / 256);
-        const int vvb = (int)((n_ + VV_THREADS - 1) / VV_THREADS);
+        const int vvb = std::min((int)((n_ + VV_THREADS - 1) / VV_THREADS), 4 * sm_count_);  // grid-stride: <= 592 partials
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
         prof_.begin(Prof::VV);
@@ -980,7 +979,7 @@ class Engine : public EngineBase {
         MB_TRY(view_in(coords, 3 * (size_t)n_, d_stage_a_, &xc));
         MB_TRY(view_in(vels, 3 * (size_t)n_, d_stage_c_, &vc));
         const int nb = (int)((n_ + 255) / 256);
-        const int vvb = (int)((n_ + VV_THREADS - 1) / VV_THREADS);
+        const int vvb = std::min((int)((n_ + VV_THREADS - 1) / VV_THREADS), 4 * sm_count_);
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
         clear_cm_kernel<T><<<1, 1, 0, stream_>>>(cm);

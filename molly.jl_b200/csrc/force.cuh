@@ -19,6 +19,12 @@
 namespace mb {
 
 constexpr int FORCE_THREADS = 256;
+#ifndef MB_LIST_BATCH
+#define MB_LIST_BATCH 8
+#endif
+#ifndef MB_MIN_BLOCKS
+#define MB_MIN_BLOCKS 4
+#endif
 
 template <typename T>
 struct ForceOut {
@@ -28,7 +34,7 @@ struct ForceOut {
 };
 
 template <typename T, int COUL, bool UNIFORM, bool SHIFT, bool ENERGY, int LPA>
-__global__ void __launch_bounds__(FORCE_THREADS)
+__global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
     brick_force_kernel(Geom<T> g, PairParams<T> P, const BrickHdr* __restrict__ hdrs, const Run* __restrict__ runs,
                        const IRow* __restrict__ irows, const typename VT<T>::T4* __restrict__ pos4,
                        const typename VT<T>::T2* __restrict__ lj2, const unsigned short* __restrict__ list,
@@ -104,24 +110,59 @@ __global__ void __launch_bounds__(FORCE_THREADS)
                 vir[3] += dx * gy; vir[4] += dx * gz; vir[5] += dy * gz;
             }
         };
+        // four neighbours at once, stage by stage, so the four shared-memory loads and the four reciprocal
+        // chains are independent and in flight together
+        auto eval4 = [&](uint2 w) {
+            int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
+            T4 pj[4];
+            T2 lj[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                pj[u] = s_pos[j[u]];
+                if (!UNIFORM) lj[u] = s_lj[j[u]];
+            }
+            T dx[4], dy[4], dz[4], r2[4], fr[4], e[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                dx[u] = pi.x - pj[u].x;
+                dy[u] = pi.y - pj[u].y;
+                dz[u] = pi.z - pj[u].z;
+                r2[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                pair_eval<T, COUL, UNIFORM, SHIFT, ENERGY, false>(P, r2[u], lj_s_i, lj_e_i, UNIFORM ? (T)0 : lj[u].x,
+                                                                  UNIFORM ? (T)0 : lj[u].y, kq_i, pj[u].w, fr[u], e[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const T gx = fr[u] * dx[u], gy = fr[u] * dy[u], gz = fr[u] * dz[u];
+                fx += gx;
+                fy += gy;
+                fz += gz;
+                if (ENERGY) {
+                    e_acc += e[u];
+                    vir[0] += dx[u] * gx; vir[1] += dy[u] * gy; vir[2] += dz[u] * gz;
+                    vir[3] += dx[u] * gy; vir[4] += dx[u] * gz; vir[5] += dy[u] * gz;
+                }
+            }
+        };
 
         // main list: groups of 32 entries; with LPA lanes each lane owns 32/LPA entries per group
         const int n_groups = ((int)cnt.x + 31) >> 5;
         const unsigned short* lp = list + (size_t)slot * g.stride;
         if (LPA == 8) {
-            // software pipeline: the indices of group gi+1 are in flight while group gi is evaluated
+            // all index words of up to LIST_BATCH groups are requested before the first one is consumed: one
+            // exposed global-memory latency per batch instead of one per group
+            constexpr int LIST_BATCH = MB_LIST_BATCH;
             const uint2* lp2 = reinterpret_cast<const uint2*>(lp) + l;
-            uint2 w = make_uint2(0u, 0u);
-            if (n_groups > 0) w = ldg_stream_u2(lp2);
-            for (int gi = 0; gi < n_groups; gi++) {
-                lp2 += 8;
-                uint2 wn = w;
-                if (gi + 1 < n_groups) wn = ldg_stream_u2(lp2);
-                eval((int)(w.x & 0xffffu), std::false_type{});
-                eval((int)(w.x >> 16), std::false_type{});
-                eval((int)(w.y & 0xffffu), std::false_type{});
-                eval((int)(w.y >> 16), std::false_type{});
-                w = wn;
+            for (int g0 = 0; g0 < n_groups; g0 += LIST_BATCH) {
+                uint2 w[LIST_BATCH];
+#pragma unroll
+                for (int u = 0; u < LIST_BATCH; u++)
+                    w[u] = (g0 + u < n_groups) ? ldg_stream_u2(lp2 + (size_t)(g0 + u) * 8) : make_uint2(0u, 0u);
+#pragma unroll
+                for (int u = 0; u < LIST_BATCH; u++)
+                    if (g0 + u < n_groups) eval4(w[u]);
             }
         } else {
             // generic: logical entry m of a group lives at ((m & 7) << 2) + (m >> 3)

@@ -28,6 +28,7 @@ struct PairParams {
     T lj_rc2, lj_rc, lj_inv_rc, lj_inv_rc2;
     T lj_w14;
     T uni_sig2, uni_eps;
+    T uni_A, uni_B;  // 48 eps sigma^12, 24 eps sigma^6 (uniform LJ, plain cutoff fast path)
     // Coulomb family
     int coul_kind;
     int coul_cut_kind;
@@ -128,7 +129,14 @@ __device__ __forceinline__ void pair_eval(const PairParams<T>& P, T r2, T lj_s_i
         eps = lj_e_i * lj_e_j;
     }
     T flj, elj = (T)0;
-    lj_term<T, SHIFT, ENERGY>(P, sig2, eps, r2, inv_r2, flj, elj);
+    if (UNIFORM && !SHIFT) {
+        // F/r = i^4 (A i^3 - B), E = i^3 (A/12 i^3 - B/6) with i = 1/r^2: two multiplies fewer than the sigma^2 form
+        const T i3 = inv_r2 * inv_r2 * inv_r2;
+        flj = (P.uni_A * i3 - P.uni_B) * (i3 * inv_r2);
+        if (ENERGY) elj = i3 * (P.uni_A * (T)(1.0 / 12.0) * i3 - P.uni_B * (T)(1.0 / 6.0));
+    } else {
+        lj_term<T, SHIFT, ENERGY>(P, sig2, eps, r2, inv_r2, flj, elj);
+    }
     if (SPECIAL) {
         flj *= P.lj_w14;
         if (ENERGY) elj *= P.lj_w14;

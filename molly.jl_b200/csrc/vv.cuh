@@ -170,9 +170,8 @@ __global__ void __launch_bounds__(VV_THREADS)
     vv_kick2_kernel(int n, T dt_half, int do_cm, double inv_total_mass, const typename VT<T>::T4* __restrict__ f4,
                     const T* __restrict__ mass, typename VT<T>::T4* __restrict__ vel4, double* __restrict__ partial,
                     Control* __restrict__ ctl, CmState<T>* __restrict__ cm, int apply_pending) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
     double px = 0, py = 0, pz = 0;
-    if (s < n) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         typename VT<T>::T4 v = vel4[s];
         if (apply_pending && cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
         const typename VT<T>::T4 f = f4[s];
@@ -180,7 +179,7 @@ __global__ void __launch_bounds__(VV_THREADS)
         v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
         vel4[s] = v;
         const T m = mass[s];
-        px = (double)(v.x * m); py = (double)(v.y * m); pz = (double)(v.z * m);
+        px += (double)(v.x * m); py += (double)(v.y * m); pz += (double)(v.z * m);
     }
     if (!do_cm) return;
     __shared__ double s_red[VV_THREADS / 32][3];

@@ -27,19 +27,41 @@ def _etol(dtype, e):
     return (1e-11 if np.dtype(dtype) == np.float64 else 2e-6) * max(abs(e), 1.0)
 
 
-def _boundary_mask(orc_factory, x64, o_inters, delta=3e-6):
-    """Atoms whose force changes when every cutoff moves by +-delta: they own a pair that sits on the cutoff
-    within f32 rounding of r^2, where a DistanceCutoff / reaction-field force is discontinuous (it jumps by
-    F(rc) ~ 1 kJ/mol/nm for CRF). The reference has the same sensitivity between its f32 and f64 paths."""
-    import copy
-    fs = []
-    for sgn in (-1.0, 1.0):
-        its = copy.deepcopy(o_inters)
-        for it in its:
-            if it.r_cut > 0:
-                it.r_cut = it.r_cut * (1.0 + sgn * delta)
-        fs.append(orc_factory(its).forces_allpairs(x64, energy=False)[0])
-    return np.abs(fs[0] - fs[1]).max(axis=1) > 1e-9, fs
+def _boundary_atoms(orc, x64, o_inters, delta=3e-6):
+    """Atoms that own a pair sitting on a cutoff within f32 rounding of r^2, where a DistanceCutoff /
+    reaction-field force is discontinuous (it jumps by F(rc) ~ 1-2 kJ/mol/nm for CRF with water charges), and
+    a bound on that jump. The reference has the same sensitivity between its f32 and f64 paths."""
+    n = len(x64)
+    count = np.zeros(n)
+    for rc in sorted({it.r_cut for it in o_inters if it.r_cut > 0}):
+        hi = orc.neighbor_list(x64, rc * (1 + delta))
+        lo = orc.neighbor_list(x64, rc * (1 - delta))
+        key = lambda a: set(map(tuple, a[:, :2].tolist()))
+        for i, j in key(hi) - key(lo):
+            count[i] += 1
+            count[j] += 1
+    return count
+
+
+def _cutoff_force_bound(sysd, o_inters):
+    """max |F(rc)| of a single pair over the interaction tuple."""
+    b = 0.0
+    qmax = np.abs(sysd["charge"]).max()
+    for it in o_inters:
+        rc = it.r_cut
+        if rc <= 0:
+            continue
+        if it.kind == o.LJ and it.cutoff_kind == o.CUT_DISTANCE:
+            sig, eps = sysd["sigma"].max(), sysd["eps"].max()
+            s6 = (sig / rc) ** 6
+            b += abs(24 * eps / rc * (2 * s6 * s6 - s6))
+        elif it.kind == o.CRF:
+            e = it.solvent_dielectric
+            krf = (1 / rc ** 3) * (e - 1) / (2 * e + 1)
+            b += it.coulomb_const * qmax * qmax * abs(1 / rc ** 2 - 2 * krf * rc)
+        elif it.kind in (o.COULOMB, o.EWALD_REAL) and it.cutoff_kind == o.CUT_DISTANCE:
+            b += it.coulomb_const * qmax * qmax / rc ** 2
+    return b
 
 
 def _check(sysd, mb_inters, o_inters, dtype, r_list=0.0, expect_path=None, label=""):
@@ -64,18 +86,18 @@ def _check(sysd, mb_inters, o_inters, dtype, r_list=0.0, expect_path=None, label
     ferr2 = np.abs(f2.astype(np.float64) - f.astype(np.float64)).max()
     print(f"    virial err={verr:.3e} (tol {vtol:.3e}) |f(force-only) - f(force+virial)|={ferr2:.3e} repeat-equal={np.array_equal(f, mb.forces(s))}")
     if np.dtype(dtype) == np.float32 and err > _tol(dtype, fmax):
-        # allow pairs sitting on the cutoff within f32 rounding to land on either side
-        mask, (f_lo, f_hi) = _boundary_mask(lambda its: H.make_oracle(sd, its, dtype=np.float64), xin.astype(np.float64), o_inters)
+        # pairs sitting on the cutoff within f32 rounding may land on either side: allow one F(rc) jump each
+        nb_pairs = _boundary_atoms(orc, xin.astype(np.float64), o_inters)
+        fc = _cutoff_force_bound(sysd, o_inters)
         per_atom = np.abs(f.astype(np.float64) - f_ref).max(axis=1)
-        alt = np.minimum(np.abs(f - f_lo).max(axis=1), np.abs(f - f_hi).max(axis=1))
-        bad = per_atom > _tol(dtype, fmax)
-        print(f"    cutoff-boundary atoms: {int(mask.sum())}; atoms over tolerance: {int(bad.sum())}; "
-              f"max err off-boundary={per_atom[~mask].max():.3e}")
-        assert not (bad & ~mask).any()
-        assert (np.minimum(per_atom, alt)[mask] <= _tol(dtype, fmax)).all()
+        allowed = _tol(dtype, fmax) + nb_pairs * fc
+        print(f"    cutoff-boundary atoms: {int((nb_pairs > 0).sum())}; atoms over the plain tolerance: "
+              f"{int((per_atom > _tol(dtype, fmax)).sum())}; F(rc) bound {fc:.3f}; "
+              f"max err off-boundary={per_atom[nb_pairs == 0].max():.3e}")
+        assert (per_atom <= allowed).all()
     else:
         assert err <= _tol(dtype, fmax)
-    assert abs(e - e_ref) <= _etol(dtype, e_ref) + (2.0 if np.dtype(dtype) == np.float32 else 0.0) * 0  # energy is continuous enough
+    assert abs(e - e_ref) <= _etol(dtype, e_ref)
     assert np.array_equal(f, mb.forces(s))  # deterministic: same kernel, no atomics
     assert ferr2 <= _tol(dtype, fmax)       # the energy/virial variant may contract FMAs differently
     assert verr <= vtol
@@ -259,7 +281,7 @@ def _pos_err(a, b, box):
 @pytest.mark.parametrize("policy", [0, 10])
 def test_vv_lj_fluid_f64_matches_oracle(policy):
     sd = H.lj_fluid(9, seed=7, dtype=np.float64, temp=120.0)
-    rc, rl, dt, n = 1.0, 1.2, 0.002, 60
+    rc, rl, dt, n = 1.0, 1.1, 0.002, 60  # skin 0.1 nm: the displacement trigger fires inside the run
     s = H.make_system(sd, (mb.LennardJones(cutoff=mb.DistanceCutoff(rc), use_neighbors=True),), np.float64, r_list=rl,
                       n_steps=policy)
     orc = H.make_oracle(sd, [o.Inter(o.LJ, o.CUT_DISTANCE, rc, use_neighbors=True)])
