@@ -1,0 +1,224 @@
+# MollyB200Ext.jl — Julia-side shim that plugs libmollyb200.so in behind Molly.jl's own API.
+#
+# Written against Molly.jl v0.23.3 (src/force.jl, src/energy.jl, src/simulators.jl, src/neighbors.jl,
+# ext/MollyCUDAExt.jl). Julia is not installed in the build image, so this file has only been checked by
+# reading; the Python mirror `molly.jl_b200/api.py` binds exactly the same C entry points and is what CI runs.
+#
+# It overrides the same generic functions that ext/MollyCUDAExt.jl overrides (SURVEY.md §8b):
+#   Molly.pairwise_forces_loop_gpu!(buffers, sys, pairwise_inters, nbs::Nothing, Val(needs_vir), step_n)   ext:845
+#   Molly.pairwise_pe_loop_gpu!(pe_vec_nounits, buffers, sys, pairwise_inters, nbs::Nothing, step_n)        ext:936
+#   Molly.simulate!(sys, sim::VelocityVerlet, n_steps; ...)                                                 simulators.jl:547
+# and falls through to the stock methods (invoke) for anything it does not recognise: non-cubic boundaries,
+# constraints, virtual sites, couplings other than AndersenThermostat, interactions outside
+# {LennardJones, Coulomb, CoulombReactionField, CoulombEwald} or unsupported cutoffs / mixing rules.
+
+module MollyB200Ext
+
+using Molly
+using CUDA
+using Random
+
+const LIB = get(ENV, "MOLLYB200_LIB", joinpath(@__DIR__, "..", "molly.jl_b200", "libmollyb200.so"))
+
+# ---- C structs (include/mollyb200.h) ------------------------------------------------------------------
+struct MBInter
+    kind::Int32
+    cutoff_kind::Int32
+    r_cut::Float64
+    r_act::Float64
+    weight_special::Float64
+    coulomb_const::Float64
+    solvent_dielectric::Float64
+    ewald_alpha::Float64
+    sigma_mix::Int32
+    eps_mix::Int32
+    approx_erfc::Int32
+    use_neighbors::Int32
+end
+
+struct MBVVParams
+    dt::Float64
+    n_steps::Int64
+    init_step::Int64
+    remove_cm_every::Int32
+    andersen_kT::Float64
+    andersen_prob::Float64
+    rng_ctr1::UInt64
+    rng_key::UInt64
+end
+
+const MB_LJ, MB_COULOMB, MB_CRF, MB_EWALD_REAL = Int32(0), Int32(1), Int32(2), Int32(3)
+const MB_CUT_NONE, MB_CUT_DISTANCE, MB_CUT_SHIFTED_POTENTIAL, MB_CUT_SHIFTED_FORCE = Int32(0), Int32(1), Int32(2), Int32(3)
+const MB_MIX_LORENTZ, MB_MIX_GEOMETRIC = Int32(0), Int32(1)
+
+function check(rc::Integer)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:mb_last_error, LIB), Cstring, ()))
+    error("libmollyb200 error $rc: $msg")   # same failure mode as ext/MollyCUDAExt.jl:733-739
+end
+
+# ---- translation of Molly interaction structs to descriptors -----------------------------------------
+cutoff_desc(::NoCutoff) = (MB_CUT_NONE, 0.0)
+cutoff_desc(c::DistanceCutoff) = (MB_CUT_DISTANCE, Float64(ustrip(c.dist_cutoff)))
+cutoff_desc(c::ShiftedPotentialCutoff) = (MB_CUT_SHIFTED_POTENTIAL, Float64(ustrip(c.dist_cutoff)))
+cutoff_desc(c::ShiftedForceCutoff) = (MB_CUT_SHIFTED_FORCE, Float64(ustrip(c.dist_cutoff)))
+cutoff_desc(::Any) = nothing
+
+mix_desc(::Molly.LorentzMixing) = MB_MIX_LORENTZ
+mix_desc(::Molly.GeometricMixing) = MB_MIX_GEOMETRIC
+mix_desc(::Any) = nothing
+
+function descriptor(inter::LennardJones)
+    cd = cutoff_desc(inter.cutoff)
+    sm, em = mix_desc(inter.σ_mixing), mix_desc(inter.ϵ_mixing)
+    (isnothing(cd) || isnothing(sm) || em != MB_MIX_GEOMETRIC) && return nothing
+    !(inter.shortcut isa Molly.LJZeroShortcut) && return nothing
+    return MBInter(MB_LJ, cd[1], cd[2], 0.0, Float64(inter.weight_special), 138.93545764, 1.0, 0.0, sm, em, 0,
+                   Int32(inter.use_neighbors))
+end
+function descriptor(inter::Coulomb)
+    cd = cutoff_desc(inter.cutoff)
+    isnothing(cd) && return nothing
+    return MBInter(MB_COULOMB, cd[1], cd[2], 0.0, Float64(inter.weight_special), Float64(ustrip(inter.coulomb_const)),
+                   1.0, 0.0, 0, 1, 0, Int32(inter.use_neighbors))
+end
+function descriptor(inter::CoulombReactionField)
+    return MBInter(MB_CRF, MB_CUT_DISTANCE, Float64(ustrip(inter.dist_cutoff)), 0.0, Float64(inter.weight_special),
+                   Float64(ustrip(inter.coulomb_const)), Float64(inter.solvent_dielectric), 0.0, 0, 1, 0,
+                   Int32(inter.use_neighbors))
+end
+descriptor(::Any) = nothing
+
+# ---- per-System context (what BuffersGPU + GPUNeighborFinder caches hold in the reference) ------------
+mutable struct Context
+    handle::Ptr{Cvoid}
+    cache_generation::Int
+end
+const CONTEXTS = IdDict{Any, Context}()
+
+function engine_eligible(sys::System{3, <:CuArray, T}, inters) where T
+    T in (Float32, Float64) || return nothing
+    sys.boundary isa CubicBoundary || return nothing
+    length(sys.constraints) == 0 || return nothing
+    isempty(sys.virtual_sites) || return nothing
+    descs = map(descriptor, inters)
+    any(isnothing, descs) && return nothing
+    return collect(MBInter, descs)
+end
+
+function context_for(sys::System{3, <:CuArray, T}, descs::Vector{MBInter}) where T
+    nf = sys.neighbor_finder
+    gen = nf isa GPUNeighborFinder ? nf.cache_generation : 0
+    ctx = get(CONTEXTS, sys.atoms, nothing)
+    if isnothing(ctx) || ctx.cache_generation != gen    # exception-list update invalidates cached masks
+        isnothing(ctx) || ccall((:mb_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx.handle)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        stream = CUDA.stream().handle
+        check(ccall((:mb_ctx_create, LIB), Cint, (Cint, Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                    CUDA.deviceid(CUDA.device()), T == Float32 ? 32 : 64, stream, h))
+        # atoms: Molly's bits layout Atom{Int32,T,T,T,T,T} is read directly from device memory
+        check(ccall((:mb_set_atoms, LIB), Cint, (Ptr{Cvoid}, Int64, CuPtr{Cvoid}), h[], length(sys.atoms),
+                    pointer(sys.atoms)))
+        side = Float64.(ustrip.(sys.boundary.side_lengths))
+        check(ccall((:mb_set_box, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), h[], collect(side)))
+        if nf isa GPUNeighborFinder
+            ei, ej = Array(nf.excluded_i), Array(nf.excluded_j)     # sparse 1-based lists, neighbors.jl:104-115
+            si, sj = Array(nf.special_i), Array(nf.special_j)
+            check(ccall((:mb_set_exceptions, LIB), Cint,
+                        (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int32}, Int64, Ptr{Int32}, Ptr{Int32}),
+                        h[], length(ei), ei, ej, length(si), si, sj))
+            check(ccall((:mb_set_neighbor_policy, LIB), Cint, (Ptr{Cvoid}, Float64, Cint), h[],
+                        Float64(ustrip(nf.dist_cutoff)), 0))
+        end
+        ctx = Context(h[], gen)
+        CONTEXTS[sys.atoms] = ctx
+    end
+    check(ccall((:mb_set_inters, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{MBInter}), ctx.handle, length(descs), descs))
+    return ctx
+end
+
+# ---- forces / energy seam -----------------------------------------------------------------------------
+function Molly.pairwise_forces_loop_gpu!(buffers, sys::System{3, <:CuArray, T}, pairwise_inters::Tuple,
+                                         nbs::Nothing, ::Val{needs_vir}, step_n) where {T, needs_vir}
+    descs = engine_eligible(sys, pairwise_inters)
+    if isnothing(descs)
+        return invoke(Molly.pairwise_forces_loop_gpu!, Tuple{Any, System{3, <:CuArray, T}, Tuple, Nothing, Val, Any},
+                      buffers, sys, pairwise_inters, nbs, Val(needs_vir), step_n)
+    end
+    ctx = context_for(sys, descs)
+    vir = needs_vir ? pointer(buffers.virial_nounits) : CU_NULL
+    # contract: ADD into buffers.fs_mat (D x N, original order) and buffers.virial_nounits
+    check(ccall((:mb_forces, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64),
+                ctx.handle, pointer(sys.coords), pointer(buffers.fs_mat), vir, step_n))
+    return buffers
+end
+
+function Molly.pairwise_pe_loop_gpu!(pe_vec_nounits, buffers, sys::System{3, <:CuArray, T}, pairwise_inters::Tuple,
+                                     nbs::Nothing, step_n) where T
+    descs = engine_eligible(sys, pairwise_inters)
+    if isnothing(descs)
+        return invoke(Molly.pairwise_pe_loop_gpu!, Tuple{Any, Any, System{3, <:CuArray, T}, Tuple, Nothing, Any},
+                      pe_vec_nounits, buffers, sys, pairwise_inters, nbs, step_n)
+    end
+    ctx = context_for(sys, descs)
+    check(ccall((:mb_energy, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64),
+                ctx.handle, pointer(sys.coords), pointer(pe_vec_nounits), step_n))
+    return pe_vec_nounits
+end
+
+# ---- simulate!(sys, ::VelocityVerlet, n) ----------------------------------------------------------------
+# Taken over only when nothing but the pairwise path contributes forces and nothing has to run on the host
+# every step; loggers fire between chunks of gcd(logger n_steps) steps (SURVEY.md Appendix A.11).
+function takeover_params(sys, sim::VelocityVerlet, n_steps, init_step, rng)
+    length(sys.specific_inter_lists) == 0 && length(sys.general_inters) == 0 || return nothing
+    kT, prob = 0.0, 0.0
+    couplings = sim.coupling isa Tuple ? sim.coupling : (sim.coupling,)
+    for c in couplings
+        c isa Molly.NoCoupling && continue
+        c isa AndersenThermostat || return nothing
+        kT = Float64(ustrip(sys.k * c.temperature))
+        prob = Float64(ustrip(sim.dt / c.coupling_const))
+    end
+    return MBVVParams(Float64(ustrip(sim.dt)), n_steps, init_step, Int32(sim.remove_CM_motion), kT, prob,
+                      rand(rng, UInt64), rand(rng, UInt64))
+end
+
+function Molly.simulate!(sys::System{3, <:CuArray, T}, sim::VelocityVerlet, n_steps::Integer;
+                         init_step=0, rng=Random.default_rng(), run_loggers=true, kwargs...) where T
+    descs = engine_eligible(sys, sys.pairwise_inters)
+    p = isnothing(descs) ? nothing : takeover_params(sys, sim, n_steps, init_step, rng)
+    if isnothing(p)
+        return invoke(Molly.simulate!, Tuple{System, VelocityVerlet, Integer}, sys, sim, n_steps;
+                      init_step=init_step, rng=rng, run_loggers=run_loggers, kwargs...)
+    end
+    ctx = context_for(sys, descs)
+    chunk = run_loggers == false || isempty(sys.loggers) ? n_steps :
+            max(1, reduce(gcd, (l.n_steps for l in values(sys.loggers))))
+    done = 0
+    Molly.apply_loggers!(sys, nothing, nothing, init_step, run_loggers)
+    while done < n_steps
+        m = min(chunk, n_steps - done)
+        pp = MBVVParams(p.dt, m, init_step + done, p.remove_cm_every, p.andersen_kT, p.andersen_prob,
+                        rand(rng, UInt64), rand(rng, UInt64))
+        check(ccall((:mb_simulate_vv, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ref{MBVVParams}),
+                    ctx.handle, pointer(sys.coords), pointer(sys.velocities), Ref(pp)))
+        done += m
+        Molly.apply_loggers!(sys, nothing, nothing, init_step + done, run_loggers)
+    end
+    return sys
+end
+
+# ---- remove_CM_motion! (ext/MollyCUDAExt.jl:2373) ---------------------------------------------------------
+function Molly.remove_CM_motion!(sys::System{3, <:CuArray, T}) where T
+    descs = engine_eligible(sys, sys.pairwise_inters)
+    isnothing(descs) && return invoke(Molly.remove_CM_motion!, Tuple{System}, sys)
+    ctx = context_for(sys, descs)
+    check(ccall((:mb_remove_cm_motion, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}), ctx.handle, pointer(sys.velocities)))
+    return sys
+end
+
+# The launch-config API of the stock extension stays callable (tests touch it, SURVEY.md §2 row 13):
+# optimize_cuda_launch_config! is a no-op here, the brick shape is chosen by the library (mb_set_launch_config).
+Molly.optimize_cuda_launch_config!(sys::System{3, <:CuArray}; kwargs...) = sys
+
+end # module
