@@ -161,14 +161,19 @@ int mb_set_launch_config(mb_ctx* ctx, const int32_t brick_dims[3], int32_t lanes
  * benchmark/gpu_profile_utils.jl:12-18); results through mb_stats. Resets the accumulators. */
 int mb_set_profiling(mb_ctx* ctx, int enable);
 
-/* Spatial decomposition over ranks (one process per GPU): the context owns the atoms whose wrapped
- * coordinates fall in brick `coord` of grid px*py*pz; halo exchange goes through callbacks the host
- * runtime provides (NCCL send/recv in the Python driver). */
-typedef struct {
-    int32_t rank, nranks;
-    int32_t grid[3];
-} mb_decomp_t;
-int mb_set_decomposition(mb_ctx* ctx, const mb_decomp_t* d);
+/* Spatial decomposition over ranks (one process per GPU; the reference has none, docs/src/documentation.md:1826).
+ * The box is cut into z-slabs of whole cell layers; a rank integrates the atoms of its slab and evaluates forces for
+ * its bricks. Per step: forward halo exchange of positions between neighbouring slabs (grouped ncclSend/ncclRecv of
+ * contiguous slot ranges, 2 cell layers each way; full-shell lists need no reverse force exchange) and one 24-byte
+ * all-reduce of sum(m v). At every rebuild (fixed interval, default 20 steps) positions and velocities are all-gathered
+ * and every rank re-sorts the replicated system identically. mb_simulate_vv takes and returns the whole system on
+ * every rank. rank 0 creates the id, the host runtime (torch.distributed / MPI) broadcasts its 128 bytes. */
+int mb_comm_unique_id(void* out128);
+int mb_comm_init(mb_ctx* ctx, const void* unique_id128, int rank, int nranks);
+/* The host-side plan of the halo exchange (no GPU needed): layer_start = ncz + 1 slot offsets of the cell layers;
+ * outputs are (peer, first slot, slot count) triples in the order the exchange posts them. */
+int mb_decomp_plan(int ncz, int halo_layers, int nranks, int rank, const int32_t* layer_start, int32_t* send_out,
+                   int32_t* n_send, int32_t* recv_out, int32_t* n_recv, int capacity);
 
 #ifdef __cplusplus
 }

@@ -16,8 +16,8 @@ EXPORTED = [
     "mb_last_error", "mb_device_count", "mb_ctx_create", "mb_ctx_destroy", "mb_set_atoms", "mb_set_atoms_soa",
     "mb_set_box", "mb_set_inters", "mb_set_exceptions", "mb_set_neighbor_policy", "mb_forces", "mb_energy",
     "mb_forces_energy", "mb_simulate_vv", "mb_remove_cm_motion", "mb_kinetic_energy", "mb_rebuild_neighbors",
-    "mb_stats", "mb_synchronize", "mb_set_capacity_scale", "mb_set_launch_config", "mb_set_decomposition",
-    "mb_set_profiling",
+    "mb_stats", "mb_synchronize", "mb_set_capacity_scale", "mb_set_launch_config", "mb_comm_unique_id",
+    "mb_comm_init", "mb_decomp_plan", "mb_set_profiling",
 ]
 
 
@@ -48,10 +48,6 @@ class MBVVParams(C.Structure):
         ("dt", C.c_double), ("n_steps", C.c_int64), ("init_step", C.c_int64), ("remove_cm_every", C.c_int32),
         ("andersen_kT", C.c_double), ("andersen_prob", C.c_double), ("rng_ctr1", C.c_uint64), ("rng_key", C.c_uint64),
     ]
-
-
-class MBDecomp(C.Structure):
-    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("grid", C.c_int32 * 3)]
 
 
 class MollyB200Error(RuntimeError):
@@ -96,7 +92,9 @@ def load():
     L.mb_synchronize.argtypes = [vp]
     L.mb_set_capacity_scale.argtypes = [vp, dbl]
     L.mb_set_launch_config.argtypes = [vp, C.POINTER(i32), i32]
-    L.mb_set_decomposition.argtypes = [vp, C.POINTER(MBDecomp)]
+    L.mb_comm_unique_id.argtypes = [vp]
+    L.mb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.mb_decomp_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(i32), vp, C.POINTER(i32), C.c_int]
     L.mb_set_profiling.argtypes = [vp, C.c_int]
     for name in EXPORTED:
         fn = getattr(L, name)

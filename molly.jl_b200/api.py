@@ -433,5 +433,30 @@ def wrap_coords(coords, boundary: CubicBoundary):
     return coords - np.floor(coords / L) * L
 
 
+def comm_unique_id() -> bytes:
+    """ncclUniqueId (128 bytes) created on the calling rank; broadcast it to the other ranks with the host runtime."""
+    buf = C.create_string_buffer(128)
+    capi.check(capi.load().mb_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(sys: System, unique_id: bytes, rank: int, nranks: int):
+    """Join the spatial decomposition: z-slabs of cell layers, NCCL halo exchange (see include/mollyb200.h)."""
+    ctx = sys.engine()
+    capi.check(sys._L.mb_comm_init(ctx, C.c_char_p(unique_id), int(rank), int(nranks)))
+
+
+def decomp_plan(ncz: int, halo_layers: int, nranks: int, rank: int, layer_start):
+    """Host-side halo-exchange plan: (send, recv) lists of (peer, first slot, slot count)."""
+    ls = np.ascontiguousarray(layer_start, np.int32)
+    cap = 4 * nranks + 8
+    snd = np.zeros((cap, 3), np.int32)
+    rcv = np.zeros((cap, 3), np.int32)
+    ns, nr = C.c_int32(0), C.c_int32(0)
+    capi.check(capi.load().mb_decomp_plan(ncz, halo_layers, nranks, rank, ls.ctypes.data, snd.ctypes.data, C.byref(ns),
+                                          rcv.ctypes.data, C.byref(nr), cap))
+    return snd[:ns.value].tolist(), rcv[:nr.value].tolist()
+
+
 def device_count() -> int:
     return int(capi.load().mb_device_count())

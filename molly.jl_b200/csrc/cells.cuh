@@ -420,11 +420,11 @@ __global__ void __launch_bounds__(256)
                        const typename VT<T>::T4* __restrict__ pos4, const int* __restrict__ orig,
                        const int* __restrict__ ex_ptr, const int* __restrict__ ex_idx, const int* __restrict__ sp_ptr,
                        const int* __restrict__ sp_idx, unsigned short* __restrict__ list,
-                       unsigned short* __restrict__ slist, ushort2* __restrict__ counts) {
+                       unsigned short* __restrict__ slist, ushort2* __restrict__ counts, int brick0) {
     if (!ctl->rebuild) return;
     using T4 = typename VT<T>::T4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = blockIdx.x;
+    const int b = blockIdx.x + brick0;
     const BrickHdr hd = hdrs[b];
     if (hd.i_count == 0 || hd.halo_count > g.halo_cap) return;
     T4* s_pos = reinterpret_cast<T4*>(smem_raw);

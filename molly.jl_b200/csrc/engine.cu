@@ -116,6 +116,100 @@ struct Prof {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so that single-GPU users do not need the library. Only what the
+// decomposed step uses: point-to-point halo exchange, grouped broadcasts, one tiny all-reduce.
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclChar = 0, ncclFloat64 = 8, ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0 } ncclRedOp_t;
+}
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+#define MB_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) return false
+        MB_SYM(GetUniqueId, "ncclGetUniqueId");
+        MB_SYM(CommInitRank, "ncclCommInitRank");
+        MB_SYM(CommDestroy, "ncclCommDestroy");
+        MB_SYM(GroupStart, "ncclGroupStart");
+        MB_SYM(GroupEnd, "ncclGroupEnd");
+        MB_SYM(Send, "ncclSend");
+        MB_SYM(Recv, "ncclRecv");
+        MB_SYM(Broadcast, "ncclBroadcast");
+        MB_SYM(AllReduce, "ncclAllReduce");
+        MB_SYM(GetErrorString, "ncclGetErrorString");
+#undef MB_SYM
+        return true;
+    }
+};
+static Nccl g_nccl;
+#define MB_NCCL(call)                                                                                       \
+    do {                                                                                                    \
+        ncclResult_t r__ = (call);                                                                          \
+        if (r__ != ncclSuccess)                                                                             \
+            return set_error(MB_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r__));          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Slab decomposition plan (pure host logic, exported as mb_decomp_plan so it can be tested without a GPU):
+// rank q owns cell layers [q*ncz/P, (q+1)*ncz/P); it needs the h layers below and above its slab (periodic).
+// Segments are contiguous slot ranges [start, start+count) taken from layer_start (ncz + 1 prefix offsets).
+// Both ends enumerate the segments of a (sender, receiver) pair in the receiver's order, so the grouped
+// ncclSend/ncclRecv calls match up.
+// ---------------------------------------------------------------------------------------------
+struct DecompSeg { int peer, start, count; };
+static inline int decomp_layer_lo(int q, int ncz, int nranks) { return (int)(((long long)q * ncz) / nranks); }
+static inline int decomp_layer_owner(int layer, int ncz, int nranks) {
+    for (int q = 0; q < nranks; q++)
+        if (layer >= decomp_layer_lo(q, ncz, nranks) && layer < decomp_layer_lo(q + 1, ncz, nranks)) return q;
+    return nranks - 1;
+}
+static void decomp_needed(int q, int ncz, int h, int nranks, std::vector<int>& out) {
+    out.clear();
+    const int lo = decomp_layer_lo(q, ncz, nranks), hi = decomp_layer_lo(q + 1, ncz, nranks);
+    std::vector<char> seen(ncz, 0);
+    for (int l = lo; l < hi; l++) seen[l] = 1;
+    for (int l = lo - h; l < lo; l++) { int w = ((l % ncz) + ncz) % ncz; if (!seen[w]) { seen[w] = 1; out.push_back(w); } }
+    for (int l = hi; l < hi + h; l++) { int w = l % ncz; if (!seen[w]) { seen[w] = 1; out.push_back(w); } }
+}
+static void decomp_plan(int ncz, int h, int nranks, int rank, const int* layer_start, std::vector<DecompSeg>& send,
+                        std::vector<DecompSeg>& recv) {
+    auto add = [&](std::vector<DecompSeg>& v, int peer, int layer) {
+        int st = layer_start[layer], cnt = layer_start[layer + 1] - st;
+        if (!v.empty() && v.back().peer == peer && v.back().start + v.back().count == st) v.back().count += cnt;
+        else v.push_back({peer, st, cnt});
+    };
+    send.clear();
+    recv.clear();
+    std::vector<int> need;
+    decomp_needed(rank, ncz, h, nranks, need);
+    for (int l : need) add(recv, decomp_layer_owner(l, ncz, nranks), l);
+    for (int q = 0; q < nranks; q++) {
+        if (q == rank) continue;
+        decomp_needed(q, ncz, h, nranks, need);
+        for (int l : need)
+            if (decomp_layer_owner(l, ncz, nranks) == rank) add(send, q, l);
+    }
+}
+
 class EngineBase {
    public:
     virtual ~EngineBase() {}
@@ -136,6 +230,7 @@ class EngineBase {
     virtual int set_capacity_scale(double s) = 0;
     virtual int set_launch_config(const int32_t bd[3], int32_t lpa) = 0;
     virtual int set_profiling(int enable) = 0;
+    virtual int comm_init(const void* uid, int rank, int nranks) = 0;
 };
 
 template <typename T>
@@ -461,6 +556,7 @@ class Engine : public EngineBase {
             vol *= box_[d];
         }
         if ((double)g.nc[0] * g.nc[1] * g.nc[2] > 2.0e8) return set_error(MB_ERR_INVALID, "cell grid too large");
+        if (nranks_ > g.nc[2]) return set_error(MB_ERR_INVALID, "more ranks than cell layers along z");
         g.ncells = g.nc[0] * g.nc[1] * g.nc[2];
         g.rlist2 = (T)(r_list_ * r_list_);
         g.skin_half2 = (T)(0.25 * skin_ * skin_);
@@ -470,6 +566,7 @@ class Engine : public EngineBase {
         int best[3] = {1, 1, 1};
         if (user_b_[0] > 0 && user_b_[1] > 0 && user_b_[2] > 0) {
             for (int d = 0; d < 3; d++) best[d] = std::min(user_b_[d], g.nc[d]);
+            if (nranks_ > 1) best[2] = 1;
         } else {
             // cost model in pair-evaluation units: every SM works through ceil(nbricks / n_sm) bricks, a brick
             // costs (owned atoms x neighbours) + ~0.5 per staged halo atom; a lone CTA per SM hides latency badly.
@@ -479,6 +576,7 @@ class Engine : public EngineBase {
                 for (int by = 1; by <= bx; by++)
                     for (int bz = 1; bz <= by; bz++) {
                         if (bx > g.nc[0] || by > g.nc[1] || bz > g.nc[2]) continue;
+                        if (nranks_ > 1 && bz != 1) continue;  // slabs are whole cell layers
                         double halo = (bx + 4.0) * (by + 4.0) * (bz + 4.0) * rho_c * 1.25 + 64;
                         double smem = halo * bytes_per_atom;
                         if (smem > smem_budget || halo > 60000) continue;
@@ -534,18 +632,79 @@ class Engine : public EngineBase {
         return MB_OK;
     }
 
+    // ---- decomposition helpers --------------------------------------------------------------------------
+    bool decomposed() const { return nranks_ > 1; }
+    int own_brick0() const { return build_nb_ < 0 ? 0 : build_b0_; }
+    int own_nbricks() const { return build_nb_ < 0 ? g_.nbricks : build_nb_; }
+    int layer_lo(int q) const { return decomp_layer_lo(q, g_.nc[2], nranks_); }
+    // slot ranges and halo segments follow from the cell layer offsets of the current sort (host copy)
+    int update_ownership() {
+        const int ncz = g_.nc[2], per_layer = g_.nc[0] * g_.nc[1];
+        layer_start_.resize(ncz + 1);
+        MB_CUDA(d_layer_start_.ensure((size_t)(ncz + 1) * sizeof(int)));
+        MB_CUDA(cudaMemcpy2DAsync(d_layer_start_.p, sizeof(int), d_cell_start_.p, (size_t)per_layer * sizeof(int), sizeof(int),
+                                  (size_t)ncz + 1, cudaMemcpyDeviceToDevice, stream_));
+        MB_CUDA(cudaMemcpyAsync(layer_start_.data(), d_layer_start_.p, (size_t)(ncz + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        const int nbxy = g_.nb[0] * g_.nb[1];
+        own_b0_ = layer_lo(rank_) * nbxy;
+        own_nb_ = (layer_lo(rank_ + 1) - layer_lo(rank_)) * nbxy;
+        own_s0_ = layer_start_[layer_lo(rank_)];
+        own_n_ = layer_start_[layer_lo(rank_ + 1)] - own_s0_;
+        decomp_plan(ncz, g_.h, nranks_, rank_, layer_start_.data(), halo_send_, halo_recv_);
+        return MB_OK;
+    }
+    // forward halo exchange of positions (x, y, z, q as 16/32-byte records): grouped NCCL send/recv between slabs
+    int halo_exchange() {
+        MB_NCCL(g_nccl.GroupStart());
+        for (auto& sg : halo_send_)
+            if (sg.count > 0) MB_NCCL(g_nccl.Send(d_pos4_.as<T4>() + sg.start, (size_t)sg.count * sizeof(T4), ncclChar, sg.peer, comm_, stream_));
+        for (auto& sg : halo_recv_)
+            if (sg.count > 0) MB_NCCL(g_nccl.Recv(d_pos4_.as<T4>() + sg.start, (size_t)sg.count * sizeof(T4), ncclChar, sg.peer, comm_, stream_));
+        MB_NCCL(g_nccl.GroupEnd());
+        return MB_OK;
+    }
+    // replicate the owned segments of positions and velocities on every rank (rebuild / export)
+    int allgather_state() {
+        MB_NCCL(g_nccl.GroupStart());
+        for (int q = 0; q < nranks_; q++) {
+            const int st = layer_start_[layer_lo(q)], cnt = layer_start_[layer_lo(q + 1)] - st;
+            if (cnt <= 0) continue;
+            MB_NCCL(g_nccl.Broadcast(d_pos4_.as<T4>() + st, d_pos4_.as<T4>() + st, (size_t)cnt * sizeof(T4), ncclChar, q, comm_, stream_));
+            MB_NCCL(g_nccl.Broadcast(d_vel4_.as<T4>() + st, d_vel4_.as<T4>() + st, (size_t)cnt * sizeof(T4), ncclChar, q, comm_, stream_));
+        }
+        MB_NCCL(g_nccl.GroupEnd());
+        return MB_OK;
+    }
+    int comm_init(const void* uid, int rank, int nranks) override {
+        if (nranks < 1 || rank < 0 || rank >= nranks || !uid) return set_error(MB_ERR_INVALID, "mb_comm_init: bad arguments");
+        if (!g_nccl.load()) return set_error(MB_ERR_INVALID, "mb_comm_init: libnccl.so.2 could not be loaded");
+        if (comm_) { g_nccl.CommDestroy(comm_); comm_ = nullptr; }
+        rank_ = rank;
+        nranks_ = nranks;
+        if (nranks > 1) {
+            ncclUniqueId id;
+            memcpy(&id, uid, sizeof(id));
+            MB_NCCL(g_nccl.CommInitRank(&comm_, nranks, id, rank));
+            MB_CUDA(d_mom_.ensure(8 * sizeof(double)));
+        }
+        have_list_ = false;
+        dirty_ = true;
+        return MB_OK;
+    }
+
     // launch the list builder (count-only or real; with or without exclusion handling)
     int launch_build(bool count_only) {
         const size_t smem = build_smem_bytes();
         const bool has_ex = !ex_ptr_.empty() || !sp_ptr_.empty();
         auto go = [&](auto kern) -> int {
             MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<g_.nbricks, 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
+            kern<<<own_nbricks(), 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
                                                      d_irows_.as<IRow>(), d_hcs_.as<ushort2>(), d_pos4_.as<T4>(), d_orig_.as<int>(),
                                                      ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(),
                                                      count_only ? nullptr : d_list_.as<unsigned short>(),
                                                      count_only ? nullptr : d_slist_.as<unsigned short>(),
-                                                     count_only ? nullptr : d_counts_.as<ushort2>());
+                                                     count_only ? nullptr : d_counts_.as<ushort2>(), own_brick0());
             return MB_OK;
         };
         if (count_only) { if (has_ex) MB_TRY(go(build_lists_kernel<T, true, true>)); else MB_TRY(go(build_lists_kernel<T, true, false>)); }
@@ -606,6 +765,7 @@ class Engine : public EngineBase {
     // coords_dev: n x 3 device array in original order.
     int first_build(const T* coords_dev) {
         const int nb = (int)((n_ + 255) / 256);
+        build_nb_ = -1;  // lists for every brick (capacities are global; mb_forces evaluates the whole box)
         init_slots_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, coords_dev, d_charge_in_.as<T>(), d_ljp_in_.as<T2>(),
                                                       d_mass_in_.as<T>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(), d_lj2_.as<T2>(),
                                                       d_orig_.as<int>(), d_inv_orig_.as<int>(), d_mass_.as<T>(), d_xref4_.as<T4>());
@@ -653,6 +813,7 @@ class Engine : public EngineBase {
             last_ctl_ = c;
             have_list_ = true;
             geom_version_++;
+            if (decomposed()) MB_TRY(update_ownership());
             return MB_OK;
         }
         return set_error(MB_ERR_CAPACITY, "could not find a brick size that fits in shared memory");
@@ -660,15 +821,15 @@ class Engine : public EngineBase {
 
     // ------------------------------------------------------------------------------------------
     template <int COUL, bool UNIFORM, bool SHIFT, bool ENERGY>
-    int launch_force_t(ForceOut<T> out) {
+    int launch_force_t(ForceOut<T> out, int brick0, int nbr) {
         const size_t smem = force_smem_bytes();
         auto launch = [&](auto kern) -> int {
             MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             prof_.begin(Prof::FORCE);
-            kern<<<g_.nbricks, FORCE_THREADS, smem, stream_>>>(g_, P_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
+            kern<<<nbr, FORCE_THREADS, smem, stream_>>>(g_, P_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
                                                                d_irows_.as<IRow>(), d_pos4_.as<T4>(), d_lj2_.as<T2>(),
                                                                d_list_.as<unsigned short>(), d_slist_.as<unsigned short>(),
-                                                               d_counts_.as<ushort2>(), out);
+                                                               d_counts_.as<ushort2>(), out, brick0);
             prof_.end(Prof::FORCE);
             return MB_OK;
         };
@@ -683,21 +844,24 @@ class Engine : public EngineBase {
         return MB_OK;
     }
     template <int COUL, bool UNIFORM>
-    int launch_force_c(bool energy, ForceOut<T> out) {
-        if (shift_) return energy ? launch_force_t<COUL, UNIFORM, true, true>(out) : launch_force_t<COUL, UNIFORM, true, false>(out);
-        return energy ? launch_force_t<COUL, UNIFORM, false, true>(out) : launch_force_t<COUL, UNIFORM, false, false>(out);
+    int launch_force_c(bool energy, ForceOut<T> out, int b0, int nbr) {
+        if (shift_) return energy ? launch_force_t<COUL, UNIFORM, true, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, true, false>(out, b0, nbr);
+        return energy ? launch_force_t<COUL, UNIFORM, false, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, false, false>(out, b0, nbr);
     }
-    int launch_force(bool energy) {
+    // owned_only: in a decomposed run the step loop evaluates only this rank's slab of bricks
+    int launch_force(bool energy, bool owned_only = false) {
+        const int b0 = owned_only ? own_b0_ : 0;
+        const int nbr = owned_only ? own_nb_ : g_.nbricks;
         ForceOut<T> out;
         out.f4 = d_f4_.as<T4>();
         out.pe_partial = d_pe_partial_.as<double>();
         out.vir_partial = d_pe_partial_.as<double>() + g_.nbricks;
         switch (P_.coul_kind) {
             case COUL_NONE:
-                return P_.uniform_lj ? launch_force_c<COUL_NONE, true>(energy, out) : launch_force_c<COUL_NONE, false>(energy, out);
-            case COUL_PLAIN: return launch_force_c<COUL_PLAIN, false>(energy, out);
-            case COUL_CRF: return launch_force_c<COUL_CRF, false>(energy, out);
-            default: return launch_force_c<COUL_EWALD, false>(energy, out);
+                return P_.uniform_lj ? launch_force_c<COUL_NONE, true>(energy, out, b0, nbr) : launch_force_c<COUL_NONE, false>(energy, out, b0, nbr);
+            case COUL_PLAIN: return launch_force_c<COUL_PLAIN, false>(energy, out, b0, nbr);
+            case COUL_CRF: return launch_force_c<COUL_CRF, false>(energy, out, b0, nbr);
+            default: return launch_force_c<COUL_EWALD, false>(energy, out, b0, nbr);
         }
     }
 
@@ -758,6 +922,13 @@ class Engine : public EngineBase {
         ingest_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_, coords_dev, vels_dev, d_orig_.as<int>(), d_xref4_.as<T4>(),
                                                   d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->rebuild);
         launches_++;
+        if (decomposed()) {
+            // every rank holds the full state here; rebuild unconditionally so that ownership is fresh
+            MB_TRY(set_flag_rebuild());
+            MB_TRY(enqueue_rebuild(true, false));
+            MB_TRY(update_ownership());
+            return MB_OK;
+        }
         MB_TRY(enqueue_rebuild(true, false));
         return MB_OK;
     }
@@ -795,6 +966,7 @@ class Engine : public EngineBase {
             MB_TRY(launch_allpairs(energy, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
             n_partials = (int)((n_ + AP_THREADS - 1) / AP_THREADS);
         } else {
+            if (decomposed()) have_list_ = false;  // forces()/potential_energy() evaluate the whole box on every rank
             MB_TRY(sync_state_from(xc, nullptr));
             MB_TRY(launch_force(energy));
             n_partials = g_.nbricks;
@@ -858,12 +1030,14 @@ class Engine : public EngineBase {
     };
     int enqueue_step(const StepCfg& c, int do_cm_now, bool clear_cm_after_k1, bool capture,
                      cudaGraphConditionalHandle handle, cudaGraph_t graph, cudaGraph_t* body_out, bool host_rebuild_hint) {
-        const int nb = (int)((n_ + 255) / 256);
-        const int vvb = std::min((int)((n_ + VV_THREADS - 1) / VV_THREADS), 4 * sm_count_);  // grid-stride: <= 592 partials
+        const bool dec = decomposed() && path_ == 1;
+        const int s0 = dec ? own_s0_ : 0, n_own = dec ? own_n_ : (int)n_;
+        const int nb = std::max(1, (n_own + 255) / 256);
+        const int vvb = std::max(1, std::min((n_own + VV_THREADS - 1) / VV_THREADS, 4 * sm_count_));  // grid-stride: <= 592 partials
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
         prof_.begin(Prof::VV);
-        vv_kick_drift_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(),
+        vv_kick_drift_kernel<T><<<nb, 256, 0, stream_>>>(s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(),
                                                          d_pos4_.as<T4>(), d_vel4_.as<T4>(), c.flag_ptr);
         prof_.end(Prof::VV);
         launches_++;
@@ -892,18 +1066,38 @@ class Engine : public EngineBase {
             MB_CUDA(cudaGraphAddNode(&cnode, graph, deps, ndeps, &cp));
             *body_out = cp.conditional.phGraph_out[0];
             MB_CUDA(cudaStreamUpdateCaptureDependencies(stream_, &cnode, 1, cudaStreamSetCaptureDependencies));
+        } else if (dec) {
+            if (host_rebuild_hint) {
+                // neighbour rebuild on a decomposed box: replicate positions and velocities, rebuild (identical sort on every
+                // rank, lists only for the owned slab), then refresh the slot ranges and halo segments
+                MB_TRY(allgather_state());
+                MB_TRY(enqueue_rebuild(true, false));
+                MB_TRY(update_ownership());
+            } else {
+                MB_TRY(halo_exchange());
+            }
         } else {
             if (rebuild_every_ == 0 || host_rebuild_hint) MB_TRY(enqueue_rebuild(true, false));
         }
+        const int s0b = dec ? own_s0_ : 0, n_ownb = dec ? own_n_ : (int)n_;  // ownership may have changed in the rebuild
+        const int nb2 = std::max(1, (n_ownb + 255) / 256);
+        const int vvb2 = std::max(1, std::min((n_ownb + VV_THREADS - 1) / VV_THREADS, 4 * sm_count_));
         if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
-        else MB_TRY(launch_force(false));
+        else MB_TRY(launch_force(false, dec));
         prof_.begin(Prof::VV);
-        vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>((int)n_, c.dt_half, do_cm_now, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
-                                                            d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0);
+        vv_kick2_kernel<T><<<vvb2, VV_THREADS, 0, stream_>>>(s0b, n_ownb, c.dt_half, do_cm_now, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
+                                                             d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0,
+                                                             dec ? d_mom_.as<double>() : nullptr);
         prof_.end(Prof::VV);
         launches_++;
+        if (dec && do_cm_now) {
+            // global sum(m v): one 24-byte all-reduce per step, then v_cm for the lazy subtraction
+            MB_NCCL(g_nccl.AllReduce(d_mom_.as<double>(), d_mom_.as<double>() + 4, 3, ncclDouble, ncclSum, comm_, stream_));
+            cm_from_sum_kernel<T><<<1, 1, 0, stream_>>>(d_mom_.as<double>() + 4, c.inv_mass, cm);
+            launches_++;
+        }
         if (c.thermostat) {
-            andersen_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, c.kT, c.prob, d_orig_.as<int>(), d_mass_.as<T>(), d_vel4_.as<T4>(), cm, ctl);
+            andersen_kernel<T><<<nb2, 256, 0, stream_>>>(s0b, n_ownb, (int)n_, c.kT, c.prob, d_orig_.as<int>(), d_mass_.as<T>(), d_vel4_.as<T4>(), cm, ctl);
             launches_++;
         }
         MB_CUDA(cudaGetLastError());
@@ -1012,13 +1206,13 @@ class Engine : public EngineBase {
         } else {
             MB_TRY(sync_state_from(xc, vc));
             c.skin_half2 = g_.skin_half2;  // geometry is chosen by the first build
-            c.flag_ptr = (rebuild_every_ == 0) ? &ctl->rebuild : &ctl->disp;
+            c.flag_ptr = (rebuild_every_ == 0 && !decomposed()) ? &ctl->rebuild : &ctl->disp;
         }
         // step bookkeeping lives on the device (tail of Control)
         {
             struct Tail { int rebuild_every; long long step, init_step; unsigned int rng[4]; } t;
             static_assert(sizeof(Tail) == sizeof(Control) - offsetof(Control, rebuild_every), "Control tail layout");
-            t.rebuild_every = rebuild_every_;
+            t.rebuild_every = (decomposed() && path_ == 1 && rebuild_every_ == 0) ? 20 : rebuild_every_;
             t.step = p->init_step;
             t.init_step = p->init_step;
             t.rng[0] = (unsigned int)p->rng_ctr1; t.rng[1] = (unsigned int)(p->rng_ctr1 >> 32);
@@ -1030,17 +1224,23 @@ class Engine : public EngineBase {
         bool cm_pending = false;  // host mirror of cm->valid
         if (p->init_step == 0 && p->remove_cm_every != 0) {
             // remove_CM_motion! before the first force evaluation (simulators.jl:563): zero-length kick
-            vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>((int)n_, (T)0, 1, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
-                                                                d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0);
+            vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>(0, (int)n_, (T)0, 1, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
+                                                                d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0, nullptr);
             launches_++;
             cm_pending = true;
         }
+        const bool dec = decomposed() && path_ == 1;
+        if (dec) {
+            // lists built from here on cover only the owned slab
+            build_b0_ = own_b0_;
+            build_nb_ = own_nb_;
+        }
         if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
-        else MB_TRY(launch_force(false));
+        else MB_TRY(launch_force(false, dec));
 
         // CUDA-graph path: static per-step sequence (remove_CM_motion in {0,1}, no stage timers requested)
         bool use_graph = graph_enabled_ && !graph_failed_ && !prof_.enabled && c.do_cm >= 0 && p->n_steps >= 4 &&
-                         !(cm_pending && c.do_cm == 0);
+                         !(cm_pending && c.do_cm == 0) && !dec;  // the decomposed step issues NCCL calls with per-rebuild sizes
         if (use_graph) {
             GraphKey key{path_, c.do_cm, c.thermostat ? 1 : 0, geom_version_, rebuild_every_, p->dt, p->andersen_kT, p->andersen_prob, n_};
             if (!graph_exec_ || !(key == graph_key_)) {
@@ -1061,11 +1261,16 @@ class Engine : public EngineBase {
                 const int64_t step_n = p->init_step + k;
                 const int do_cm = (p->remove_cm_every != 0 && step_n % p->remove_cm_every == 0) ? 1 : 0;
                 const bool clear_after_k1 = cm_pending && !do_cm;  // K1 consumed v_cm; nothing overwrites it this step
-                const bool hint = rebuild_every_ > 0 && k > 1 && (step_n - 1) % rebuild_every_ == 0;
+                const int every = (dec && rebuild_every_ == 0) ? 20 : rebuild_every_;  // decomposed runs use a fixed interval
+                const bool hint = every > 0 && k > 1 && (step_n - 1) % every == 0;
                 MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint));
                 cm_pending = (do_cm != 0) && !c.thermostat;
                 n_steps_++;
             }
+        }
+        if (dec) {
+            MB_TRY(allgather_state());  // every rank returns the whole system
+            build_nb_ = -1;
         }
         // export
         T* xo = c_dev ? reinterpret_cast<T*>(coords) : d_stage_a_.as<T>();
@@ -1191,6 +1396,15 @@ class Engine : public EngineBase {
     GraphKey graph_key_;
     bool graph_enabled_ = true, graph_failed_ = false, graph_used_ = false, own_stream_ = false;
     int geom_version_ = 0;
+    // spatial decomposition (z-slabs of cell layers; one rank per GPU)
+    ncclComm_t comm_ = nullptr;
+    int rank_ = 0, nranks_ = 1;
+    int own_b0_ = 0, own_nb_ = 0;        // this rank's bricks (static for a geometry)
+    int build_b0_ = 0, build_nb_ = -1;   // brick range the list builder covers (-1 = all)
+    int own_s0_ = 0, own_n_ = 0;         // this rank's slots (changes at every rebuild)
+    std::vector<int> layer_start_;       // slot index of the first atom of every cell layer (ncz + 1)
+    std::vector<DecompSeg> halo_send_, halo_recv_;
+    DevBuf d_layer_start_, d_mom_;
     DevBuf d_mass_in_, d_charge_in_, d_ljp_in_;
     DevBuf d_pos4_, d_vel4_, d_f4_, d_xref4_, d_lj2_, d_orig_, d_inv_orig_, d_mass_;
     DevBuf d_pos4_t_, d_vel4_t_, d_lj2_t_, d_orig_t_, d_mass_t_;
@@ -1301,10 +1515,30 @@ int mb_set_launch_config(mb_ctx* ctx, const int32_t brick_dims[3], int32_t lanes
     return ctx->e->set_launch_config(brick_dims, lanes_per_atom);
 }
 int mb_set_profiling(mb_ctx* ctx, int enable) { MB_CTX_GUARD(ctx); return ctx->e->set_profiling(enable); }
-int mb_set_decomposition(mb_ctx* ctx, const mb_decomp_t* d) {
+int mb_comm_unique_id(void* out128) {
+    if (!out128) return mb::set_error(MB_ERR_INVALID, "null output");
+    if (!mb::g_nccl.load()) return mb::set_error(MB_ERR_INVALID, "libnccl.so.2 could not be loaded");
+    mb::ncclUniqueId id;
+    if (mb::g_nccl.GetUniqueId(&id) != mb::ncclSuccess) return mb::set_error(MB_ERR_CUDA, "ncclGetUniqueId failed");
+    memcpy(out128, &id, sizeof(id));
+    return MB_OK;
+}
+int mb_decomp_plan(int ncz, int halo_layers, int nranks, int rank, const int32_t* layer_start, int32_t* send_out, int32_t* n_send,
+                   int32_t* recv_out, int32_t* n_recv, int capacity) {
+    if (ncz < 1 || nranks < 1 || nranks > ncz || rank < 0 || rank >= nranks || !layer_start || !send_out || !recv_out || !n_send || !n_recv)
+        return mb::set_error(MB_ERR_INVALID, "mb_decomp_plan: bad arguments");
+    std::vector<mb::DecompSeg> snd, rcv;
+    mb::decomp_plan(ncz, halo_layers, nranks, rank, layer_start, snd, rcv);
+    if ((int)snd.size() > capacity || (int)rcv.size() > capacity) return mb::set_error(MB_ERR_CAPACITY, "mb_decomp_plan: capacity");
+    for (size_t k = 0; k < snd.size(); k++) { send_out[3 * k] = snd[k].peer; send_out[3 * k + 1] = snd[k].start; send_out[3 * k + 2] = snd[k].count; }
+    for (size_t k = 0; k < rcv.size(); k++) { recv_out[3 * k] = rcv[k].peer; recv_out[3 * k + 1] = rcv[k].start; recv_out[3 * k + 2] = rcv[k].count; }
+    *n_send = (int32_t)snd.size();
+    *n_recv = (int32_t)rcv.size();
+    return MB_OK;
+}
+int mb_comm_init(mb_ctx* ctx, const void* unique_id128, int rank, int nranks) {
     MB_CTX_GUARD(ctx);
-    (void)d;
-    return mb::set_error(MB_ERR_INVALID, "spatial decomposition is driven by the host runtime (see DESIGN.md); not available in this build");
+    return ctx->e->comm_init(unique_id128, rank, nranks);
 }
 
 }  // extern "C"

@@ -38,11 +38,12 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
     brick_force_kernel(Geom<T> g, PairParams<T> P, const BrickHdr* __restrict__ hdrs, const Run* __restrict__ runs,
                        const IRow* __restrict__ irows, const typename VT<T>::T4* __restrict__ pos4,
                        const typename VT<T>::T2* __restrict__ lj2, const unsigned short* __restrict__ list,
-                       const unsigned short* __restrict__ slist, const ushort2* __restrict__ counts, ForceOut<T> out) {
+                       const unsigned short* __restrict__ slist, const ushort2* __restrict__ counts, ForceOut<T> out,
+                       int brick0) {
     using T4 = typename VT<T>::T4;
     using T2 = typename VT<T>::T2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = blockIdx.x;
+    const int b = blockIdx.x + brick0;  // brick0: first brick of this rank's slab (0 on a single GPU)
     const BrickHdr hd = hdrs[b];
     const int tid = threadIdx.x;
     if (hd.i_count == 0 || hd.halo_count > g.halo_cap) {

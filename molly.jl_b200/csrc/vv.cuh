@@ -129,12 +129,13 @@ __global__ void scatter_forces_kernel(int n, const typename VT<T>::T4* __restric
 
 // ---- K1: first half kick + drift + displacement check ------------------------------------------
 template <typename T>
-__global__ void vv_kick_drift_kernel(int n, T dt, T dt_half, T skin_half2, const CmState<T>* __restrict__ cm,
+__global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half2, const CmState<T>* __restrict__ cm,
                                      const typename VT<T>::T4* __restrict__ f4,
                                      const typename VT<T>::T4* __restrict__ xref4, typename VT<T>::T4* __restrict__ pos4,
                                      typename VT<T>::T4* __restrict__ vel4, int* __restrict__ flag) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
+    s += s0;  // [s0, s0 + n): the slots this rank owns
     typename VT<T>::T4 v = vel4[s];
     const typename VT<T>::T4 f = f4[s];
     typename VT<T>::T4 p = pos4[s];
@@ -167,11 +168,11 @@ __global__ void decide_kernel(Control* ctl, cudaGraphConditionalHandle handle, i
 constexpr int VV_THREADS = 256;
 template <typename T>
 __global__ void __launch_bounds__(VV_THREADS)
-    vv_kick2_kernel(int n, T dt_half, int do_cm, double inv_total_mass, const typename VT<T>::T4* __restrict__ f4,
+    vv_kick2_kernel(int s0, int n, T dt_half, int do_cm, double inv_total_mass, const typename VT<T>::T4* __restrict__ f4,
                     const T* __restrict__ mass, typename VT<T>::T4* __restrict__ vel4, double* __restrict__ partial,
-                    Control* __restrict__ ctl, CmState<T>* __restrict__ cm, int apply_pending) {
+                    Control* __restrict__ ctl, CmState<T>* __restrict__ cm, int apply_pending, double* __restrict__ mom_out) {
     double px = 0, py = 0, pz = 0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    for (int s = s0 + blockIdx.x * blockDim.x + threadIdx.x; s < s0 + n; s += gridDim.x * blockDim.x) {
         typename VT<T>::T4 v = vel4[s];
         if (apply_pending && cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
         const typename VT<T>::T4 f = f4[s];
@@ -223,12 +224,24 @@ __global__ void __launch_bounds__(VV_THREADS)
         if (tid == 0) {
             a = b = c = 0;
             for (int w = 0; w < VV_THREADS / 32; w++) { a += s_red[w][0]; b += s_red[w][1]; c += s_red[w][2]; }
-            cm->v[0] = (T)(a * inv_total_mass);
-            cm->v[1] = (T)(b * inv_total_mass);
-            cm->v[2] = (T)(c * inv_total_mass);
-            cm->valid = 1;
+            if (mom_out) {  // decomposed run: publish this rank's sum(m v); the all-reduce and cm_from_sum_kernel finish it
+                mom_out[0] = a; mom_out[1] = b; mom_out[2] = c;
+            } else {
+                cm->v[0] = (T)(a * inv_total_mass);
+                cm->v[1] = (T)(b * inv_total_mass);
+                cm->v[2] = (T)(c * inv_total_mass);
+                cm->valid = 1;
+            }
         }
     }
+}
+
+template <typename T>
+__global__ void cm_from_sum_kernel(const double* __restrict__ mom_sum, double inv_total_mass, CmState<T>* cm) {
+    cm->v[0] = (T)(mom_sum[0] * inv_total_mass);
+    cm->v[1] = (T)(mom_sum[1] * inv_total_mass);
+    cm->v[2] = (T)(mom_sum[2] * inv_total_mass);
+    cm->valid = 1;
 }
 
 // stand-alone momentum pass (remove_CM_motion! before the first step): same reduction, no kick
@@ -245,13 +258,13 @@ __global__ void clear_cm_kernel(CmState<T>* cm) {
 // order; normals by Box-Muller. Statistical parity only (the reference's normal transform lives in
 // the un-vendored PhiloxRNG.jl). Consumes the pending v_cm.
 template <typename T>
-__global__ void andersen_kernel(int n, T kT, double prob, const int* __restrict__ orig,
+__global__ void andersen_kernel(int s0, int n_own, int n, T kT, double prob, const int* __restrict__ orig,
                                 const T* __restrict__ mass, typename VT<T>::T4* __restrict__ vel4,
                                 CmState<T>* __restrict__ cm, Control* __restrict__ ctl) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ctr1_lo = ctl->rng[0], ctr1_hi = ctl->rng[1], key_lo = ctl->rng[2], key_hi = ctl->rng[3];
     const uint32_t step_lo = (uint32_t)ctl->step;
-    if (s < n) {
+    if (s < s0 + n_own) {
         typename VT<T>::T4 v = vel4[s];
         if (cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
         uint32_t c[4] = {(uint32_t)(orig[s] + 1), step_lo, ctr1_lo, ctr1_hi};
