@@ -62,17 +62,15 @@ def workload(name: str, dtype):
         return sd, inters, ointers, 0.002, rc, "1M-atom LJ fluid, cubic PBC, 1.2nm cutoff, Float32"
     if name == "c3":
         g = dict(np.load(os.path.join(ROOT, "tests", "golden", "6mrr.npz")))
-        box = g["box"]
-        x = g["coords"] - np.floor(g["coords"] / box) * box
-        sd = dict(n=len(x), box=box, coords=x.astype(dtype), velocities=g["velocities_300K"].astype(dtype),
-                  mass=g["mass"], charge=g["charge"], sigma=g["sigma"], eps=g["eps"], excluded=g["excluded"],
-                  special=g["special"])
+        sd = H.sixmrr_description(g)
+        sd = dict(sd, coords=sd["coords"].astype(dtype), velocities=sd["velocities"].astype(dtype), golden=g)
         w_lj, w_c = float(g["lj14scale"]), float(g["coulomb14scale"])
         inters = (mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True, weight_special=w_lj),
                   mb.CoulombReactionField(dist_cutoff=1.0, use_neighbors=True, weight_special=w_c))
         ointers = [o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=w_lj, use_neighbors=True),
                    o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=w_c, use_neighbors=True)]
-        return sd, inters, ointers, 0.0005, 1.0, "6mrr solvated protein (15 954 atoms), LJ+CRF non-bonded only, Float32"
+        return sd, inters, ointers, 0.0005, 1.0, ("6mrr solvated protein (15 954 atoms), AMBER ff99SBildn + TIP3P, LJ + "
+                                                  "CoulombReactionField + bonds/angles/torsions, VelocityVerlet + Andersen, Float32")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -151,6 +149,12 @@ def ncu_traffic(workload_name: str):
 def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32):
     """Molly-algorithm CPU restatement (oracle): list every 10 steps with rc + 0.2 nm, all host threads."""
     from oracle import oracle as o
+    if "golden" in sd:  # 6mrr: pairwise in C (threaded), bonded terms in numpy, f64
+        t0 = time.perf_counter()
+        H.oracle_vv_with_bonded(sd["golden"], sd["coords"].astype(np.float64), sd["velocities"].astype(np.float64), dt, steps,
+                                r_list=rc + 0.2, nl_every=10)
+        t = time.perf_counter() - t0
+        return steps / t, o.max_threads(), t
     orc = H.make_oracle(sd, ointers, dtype=dtype)
     nt = o.max_threads()
     x, v = sd["coords"].astype(dtype), sd["velocities"].astype(dtype)
@@ -193,7 +197,7 @@ def main():
             return
         sd, inters, ointers, dt, rc, label = workload(wl, dtype)
         steps = args.steps if args.steps is not None else (10 if wl != "c3" else 100)
-        steps = min(steps, 20 if wl == "c2" else (5 if wl == "c4" else 400))  # bounded sample
+        steps = min(steps, 20 if wl == "c2" else (5 if wl == "c4" else 60))  # bounded sample
         warm = min(args.warmup if args.warmup is not None else 1, 2)
         sps, nt, t = run_cpu(sd, ointers, dt, rc, steps, warm)
         out = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
@@ -232,8 +236,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     xs = torch.from_numpy(sd["coords"].astype(dtype)).to(dev).contiguous()
     vs = torch.from_numpy(sd["velocities"].astype(dtype)).to(dev).contiguous()
+    specific = H.sixmrr_specific_lists(sd["golden"]) if "golden" in sd else ()
     sysm = mb.System(atoms=atoms, coords=xs, boundary=mb.CubicBoundary(*sd["box"]), velocities=vs, pairwise_inters=inters,
-                     neighbor_finder=nf, dtype=dtype, device=local_rank)
+                     neighbor_finder=nf, dtype=dtype, device=local_rank, specific_inter_lists=specific)
     sysm.engine()
     if any(args.brick) or args.lanes:
         sysm.set_launch_config(tuple(args.brick), args.lanes)
@@ -243,7 +248,8 @@ def main():
         uid = [mb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         mb.comm_init(sysm, uid[0], rank, world)
-    sim = mb.VelocityVerlet(dt=dt, remove_CM_motion=1)
+    coupling = mb.AndersenThermostat(300.0, 1.0) if wl == "c3" else None  # config 3: VelocityVerlet + Andersen
+    sim = mb.VelocityVerlet(dt=dt, coupling=coupling, remove_CM_motion=1)
     rng = np.random.default_rng(1234 + rank)
 
     def barrier():
@@ -295,7 +301,8 @@ def main():
         hx.copy_(xs.cpu())
         hv.copy_(vs.cpu())
         hsys = mb.System(atoms=atoms, coords=hx.numpy(), boundary=mb.CubicBoundary(*sd["box"]), velocities=hv.numpy(),
-                         pairwise_inters=inters, neighbor_finder=nf, dtype=dtype, device=local_rank)
+                         pairwise_inters=inters, neighbor_finder=nf, dtype=dtype, device=local_rank,
+                         specific_inter_lists=specific)
         hsys.engine()
         if any(args.brick) or args.lanes:
             hsys.set_launch_config(tuple(args.brick), args.lanes)
@@ -326,7 +333,7 @@ def main():
     # ---- CPU baseline on rank 0 (bounded sample)
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        cs = args.cpu_steps or (10 if wl == "c2" else (3 if wl == "c4" else 200))
+        cs = args.cpu_steps or (10 if wl == "c2" else (3 if wl == "c4" else 40))
         sps, nt, t = run_cpu(sd, ointers, dt, rc, cs, 1)
         cpu = {"value": sps, "unit": UNIT, "cores": nt, "kind": "port",
                "sample": f"{cs} MD steps of the same workload in {t:.1f} s (oracle restatement of Molly's threaded CPU path, "

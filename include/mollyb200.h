@@ -125,6 +125,16 @@ int mb_energy(mb_ctx* ctx, const void* coords, void* pe, int64_t step_n);
 int mb_forces_energy(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, void* virial,
                      int64_t step_n);
 
+/* Specific (bonded) interaction lists, SURVEY.md §8(f)-1: InteractionList{2,3,4}Atoms (src/types.jl:89-157) with
+ * HarmonicBond (kind 0; params k, r0), HarmonicAngle (kind 1; k, theta0), PeriodicTorsion (kind 2; one
+ * (periodicity, phase, k) term per entry — a torsion with several terms is listed several times; impropers are the
+ * same struct, src/interactions/periodic_torsion.jl:17-142). atom_idx: n_terms x (kind + 2), 1-based; params: double,
+ * n_terms x 2 or 3. Host pointers. They are evaluated inside mb_simulate_vv (specific_forces_gpu!, src/force.jl:1231)
+ * and by mb_forces_energy_all; mb_forces / mb_energy stay pairwise-only (the pairwise_*_loop_gpu! seam). */
+int mb_set_specific(mb_ctx* ctx, int kind, int64_t n_terms, const int32_t* atom_idx, const double* params);
+/* forces(sys) / potential_energy(sys) of pairwise + specific interactions in one call (ADD semantics). */
+int mb_forces_energy_all(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, int64_t step_n);
+
 /* simulate!(sys, VelocityVerlet(dt, coupling, remove_CM_motion), n_steps) hot loop
  * (src/simulators.jl:547-668): wrap, [CM removal when init_step==0], neighbours, F0, then n_steps of
  * kick / drift / wrap / forces / kick / CM removal (every remove_cm_every steps; 0 = never) /

@@ -12,4 +12,5 @@ from .api import (Atom, CubicBoundary, System, NoCutoff, DistanceCutoff, Shifted
                   VelocityVerlet, forces, forces_virial, potential_energy, forces_energy, find_neighbors, simulate,
                   kinetic_energy, temperature, remove_CM_motion, random_velocities, wrap_coords, device_count,
                   atoms_from_arrays, atoms_to_array, atom_dtype, MollyB200Error, COULOMB_CONST, BOLTZMANN_K,
-                  comm_unique_id, comm_init, decomp_plan)
+                  comm_unique_id, comm_init, decomp_plan, InteractionList2Atoms, InteractionList3Atoms,
+                  InteractionList4Atoms)

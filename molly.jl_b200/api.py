@@ -206,6 +206,58 @@ TreeNeighborFinder = GPUNeighborFinder
 
 
 @dataclass
+class InteractionList2Atoms:
+    """InteractionList2Atoms of HarmonicBond (src/types.jl:89-157, interactions/harmonic_bond.jl): 1-based is/js,
+    per-term k (kJ mol^-1 nm^-2) and r0 (nm)."""
+    is_: object
+    js: object
+    k: object
+    r0: object
+    kind = 0
+
+    def arrays(self):
+        idx = np.stack([np.asarray(self.is_), np.asarray(self.js)], 1).astype(np.int32)
+        par = np.stack([np.asarray(self.k, np.float64), np.asarray(self.r0, np.float64)], 1)
+        return np.ascontiguousarray(idx), np.ascontiguousarray(par)
+
+
+@dataclass
+class InteractionList3Atoms:
+    """InteractionList3Atoms of HarmonicAngle (interactions/harmonic_angle.jl): k (kJ mol^-1 rad^-2), theta0 (rad)."""
+    is_: object
+    js: object
+    ks: object
+    k: object
+    theta0: object
+    kind = 1
+
+    def arrays(self):
+        idx = np.stack([np.asarray(self.is_), np.asarray(self.js), np.asarray(self.ks)], 1).astype(np.int32)
+        par = np.stack([np.asarray(self.k, np.float64), np.asarray(self.theta0, np.float64)], 1)
+        return np.ascontiguousarray(idx), np.ascontiguousarray(par)
+
+
+@dataclass
+class InteractionList4Atoms:
+    """InteractionList4Atoms of PeriodicTorsion (interactions/periodic_torsion.jl), flattened to one
+    (periodicity, phase, k) term per entry; propers and impropers use the same list type."""
+    is_: object
+    js: object
+    ks: object
+    ls: object
+    periodicity: object
+    phase: object
+    k: object
+    kind = 2
+
+    def arrays(self):
+        idx = np.stack([np.asarray(self.is_), np.asarray(self.js), np.asarray(self.ks), np.asarray(self.ls)], 1).astype(np.int32)
+        par = np.stack([np.asarray(self.periodicity, np.float64), np.asarray(self.phase, np.float64),
+                        np.asarray(self.k, np.float64)], 1)
+        return np.ascontiguousarray(idx), np.ascontiguousarray(par)
+
+
+@dataclass
 class AndersenThermostat:
     temperature: float
     coupling_const: float
@@ -229,7 +281,7 @@ class System:
     """
 
     def __init__(self, atoms, coords, boundary, velocities=None, pairwise_inters=(), neighbor_finder=None,
-                 dtype=np.float32, device: int = 0, k=BOLTZMANN_K):
+                 dtype=np.float32, device: int = 0, k=BOLTZMANN_K, specific_inter_lists=()):
         self.dtype = np.dtype(dtype)
         if isinstance(atoms, np.ndarray) and atoms.dtype.names:
             self.atoms = np.ascontiguousarray(atoms.astype(atom_dtype(self.dtype)))
@@ -241,6 +293,7 @@ class System:
         self.velocities = self._as_state(velocities if velocities is not None else np.zeros((self.n, 3)))
         self.pairwise_inters = tuple(pairwise_inters)
         self.neighbor_finder = neighbor_finder
+        self.specific_inter_lists = tuple(specific_inter_lists)
         self.device = device
         self.k = k
         self._ctx = None
@@ -286,6 +339,15 @@ class System:
             capi.check(L.mb_set_exceptions(ctx, len(ei), ei.ctypes.data, ej.ctypes.data, len(si), si.ctypes.data,
                                            sj.ctypes.data))
             capi.check(L.mb_set_neighbor_policy(ctx, float(nf.dist_cutoff), int(nf.n_steps)))
+        # specific interaction lists: entries of the same kind are concatenated (e.g. propers + impropers)
+        by_kind = {}
+        for sil in self.specific_inter_lists:
+            idx, par = sil.arrays()
+            a, b = by_kind.get(sil.kind, (None, None))
+            by_kind[sil.kind] = (idx if a is None else np.concatenate([a, idx]), par if b is None else np.concatenate([b, par]))
+        for kind, (idx, par) in by_kind.items():
+            idx, par = np.ascontiguousarray(idx), np.ascontiguousarray(par)
+            capi.check(L.mb_set_specific(ctx, kind, len(idx), idx.ctypes.data, par.ctypes.data))
 
     def close(self):
         if self._ctx is not None:
@@ -351,10 +413,14 @@ def potential_energy(sys: System, neighbors=None, step_n: int = 0) -> float:
 
 
 def forces_energy(sys: System, step_n: int = 0):
+    """forces(sys) and potential_energy(sys) of all pairwise + specific interactions in one traversal."""
     ctx = sys.engine()
     fs = np.zeros((sys.n, 3), sys.dtype)
     pe = np.zeros(1, sys.dtype)
-    capi.check(sys._L.mb_forces_energy(ctx, _ptr(sys.coords), fs.ctypes.data, pe.ctypes.data, None, step_n))
+    if sys.specific_inter_lists:
+        capi.check(sys._L.mb_forces_energy_all(ctx, _ptr(sys.coords), fs.ctypes.data, pe.ctypes.data, step_n))
+    else:
+        capi.check(sys._L.mb_forces_energy(ctx, _ptr(sys.coords), fs.ctypes.data, pe.ctypes.data, None, step_n))
     return fs, float(pe[0])
 
 

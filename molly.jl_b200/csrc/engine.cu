@@ -8,6 +8,7 @@
 #include <type_traits>
 
 #include "../../include/mollyb200.h"
+#include "bonded.cuh"
 #include "cells.cuh"
 #include "common.cuh"
 #include "force.cuh"
@@ -220,7 +221,7 @@ class EngineBase {
     virtual int set_exceptions(int64_t ne, const int32_t* ei, const int32_t* ej, int64_t ns, const int32_t* si,
                                const int32_t* sj) = 0;
     virtual int set_neighbor_policy(double r_list, int rebuild_every) = 0;
-    virtual int forces_energy(const void* coords, void* fs, void* pe, void* vir, int64_t step_n) = 0;
+    virtual int forces_energy(const void* coords, void* fs, void* pe, void* vir, int64_t step_n, bool with_specific) = 0;
     virtual int simulate_vv(void* coords, void* vels, const mb_vv_params_t* p) = 0;
     virtual int remove_cm(void* vels) = 0;
     virtual int kinetic_energy(const void* vels, double* out) = 0;
@@ -231,6 +232,7 @@ class EngineBase {
     virtual int set_launch_config(const int32_t bd[3], int32_t lpa) = 0;
     virtual int set_profiling(int enable) = 0;
     virtual int comm_init(const void* uid, int rank, int nranks) = 0;
+    virtual int set_specific(int kind, int64_t n, const int32_t* idx, const double* par) = 0;
 };
 
 template <typename T>
@@ -632,6 +634,67 @@ class Engine : public EngineBase {
         return MB_OK;
     }
 
+    // ---- specific (bonded) interaction lists: kind 0 bond (k, r0), 1 angle (k, theta0), 2 torsion (periodicity, phase, k)
+    int set_specific(int kind, int64_t n, const int32_t* idx, const double* par) override {
+        if (kind < 0 || kind > 2 || n < 0 || (n > 0 && (!idx || !par))) return set_error(MB_ERR_INVALID, "mb_set_specific: bad arguments");
+        if (n_ <= 0) return set_error(MB_ERR_STATE, "mb_set_specific: set atoms first");
+        const int na = kind + 2, np_ = (kind == 2) ? 3 : 2;
+        std::vector<int> hidx((size_t)n * na);
+        std::vector<T> hpar((size_t)n * np_);
+        for (int64_t t = 0; t < n * na; t++) {
+            int a = idx[t] - 1;  // 1-based in, like InteractionList{2,3,4}Atoms (src/types.jl:89-157)
+            if (a < 0 || a >= n_) return set_error(MB_ERR_INVALID, "mb_set_specific: atom index out of bounds");
+            hidx[t] = a;
+        }
+        for (int64_t t = 0; t < n * np_; t++) hpar[t] = (T)par[t];
+        sp_n_[kind] = n;
+        if (n > 0) {
+            MB_CUDA(d_sp_idx_k_[kind].ensure(hidx.size() * sizeof(int)));
+            MB_CUDA(d_sp_par_k_[kind].ensure(hpar.size() * sizeof(T)));
+            MB_CUDA(cudaMemcpy(d_sp_idx_k_[kind].p, hidx.data(), hidx.size() * sizeof(int), cudaMemcpyHostToDevice));
+            MB_CUDA(cudaMemcpy(d_sp_par_k_[kind].p, hpar.data(), hpar.size() * sizeof(T), cudaMemcpyHostToDevice));
+        }
+        int64_t mx = std::max(sp_n_[0], std::max(sp_n_[1], sp_n_[2]));
+        MB_CUDA(d_sp_partial_.ensure((size_t)(3 * ((mx + BONDED_THREADS - 1) / BONDED_THREADS) + 8) * sizeof(double)));
+        destroy_graph();  // the step graph bakes the term counts in
+        return MB_OK;
+    }
+    bool has_specific() const { return sp_n_[0] + sp_n_[1] + sp_n_[2] > 0; }
+    // add the bonded forces to f4 (slot order on the brick path, original order on the all-pairs path);
+    // with energy: per-kernel partials are summed into d_sp_energy_ (double, device)
+    int launch_bonded(bool energy) {
+        if (!has_specific()) return MB_OK;
+        const int* slot_of = (path_ == 1) ? d_inv_orig_.as<int>() : nullptr;
+        BoxT bx;
+        for (int d = 0; d < 3; d++) bx.L[d] = box_[d];
+        if (energy) {
+            MB_CUDA(d_sp_energy_.ensure(sizeof(double)));
+            MB_CUDA(cudaMemsetAsync(d_sp_energy_.p, 0, sizeof(double), stream_));
+        }
+        double* part = d_sp_partial_.as<double>();
+        for (int kind = 0; kind < 3; kind++) {
+            const int n = (int)sp_n_[kind];
+            if (n == 0) continue;
+            const int nblk = (n + BONDED_THREADS - 1) / BONDED_THREADS;
+            const int* idx = d_sp_idx_k_[kind].as<int>();
+            const T* par = d_sp_par_k_[kind].as<T>();
+#define MB_BONDED(KERN)                                                                                                  \
+    if (energy) KERN<T, true><<<nblk, BONDED_THREADS, 0, stream_>>>(n, idx, par, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part); \
+    else KERN<T, false><<<nblk, BONDED_THREADS, 0, stream_>>>(n, idx, par, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part)
+            if (kind == 0) { MB_BONDED(bond_kernel); }
+            else if (kind == 1) { MB_BONDED(angle_kernel); }
+            else { MB_BONDED(torsion_kernel); }
+#undef MB_BONDED
+            launches_++;
+            if (energy) {
+                sum_partials_kernel<<<1, 256, 0, stream_>>>(nblk, part, d_sp_energy_.as<double>());
+                launches_++;
+            }
+        }
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
+
     // ---- decomposition helpers --------------------------------------------------------------------------
     bool decomposed() const { return nranks_ > 1; }
     int own_brick0() const { return build_nb_ < 0 ? 0 : build_b0_; }
@@ -947,7 +1010,7 @@ class Engine : public EngineBase {
     }
 
     // ------------------------------------------------------------------------------------------
-    int forces_energy(const void* coords, void* fs, void* pe, void* vir, int64_t step_n) override {
+    int forces_energy(const void* coords, void* fs, void* pe, void* vir, int64_t step_n, bool with_specific) override {
         (void)step_n;
         MB_TRY(prepare());
         if (!coords) return set_error(MB_ERR_INVALID, "coords is null");
@@ -972,6 +1035,7 @@ class Engine : public EngineBase {
             n_partials = g_.nbricks;
             orig = d_orig_.as<int>();
         }
+        if (with_specific) MB_TRY(launch_bonded(pe != nullptr));
         // outputs (ADD semantics)
         if (fs) {
             if (is_device_ptr(fs)) {
@@ -1005,6 +1069,10 @@ class Engine : public EngineBase {
             double* pp = d_pe_partial_.as<double>();
             reduce_partials_kernel<T><<<1, 256, 0, stream_>>>(n_partials, pp, pp + n_partials, pe_target, vir_target, nullptr);
             launches_++;
+            if (with_specific && has_specific() && pe_target) {
+                add_double_kernel<T><<<1, 1, 0, stream_>>>(d_sp_energy_.as<double>(), pe_target);
+                launches_++;
+            }
             if ((pe && !pe_dev) || (vir && !vir_dev)) {
                 MB_CUDA(cudaMemcpyAsync(host_sc, d_scalars_.p, 16 * sizeof(T), cudaMemcpyDeviceToHost, stream_));
                 MB_CUDA(cudaStreamSynchronize(stream_));
@@ -1084,6 +1152,7 @@ class Engine : public EngineBase {
         const int vvb2 = std::max(1, std::min((n_ownb + VV_THREADS - 1) / VV_THREADS, 4 * sm_count_));
         if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
         else MB_TRY(launch_force(false, dec));
+        MB_TRY(launch_bonded(false));
         prof_.begin(Prof::VV);
         vv_kick2_kernel<T><<<vvb2, VV_THREADS, 0, stream_>>>(s0b, n_ownb, c.dt_half, do_cm_now, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
                                                              d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0,
@@ -1237,6 +1306,7 @@ class Engine : public EngineBase {
         }
         if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
         else MB_TRY(launch_force(false, dec));
+        MB_TRY(launch_bonded(false));
 
         // CUDA-graph path: static per-step sequence (remove_CM_motion in {0,1}, no stage timers requested)
         bool use_graph = graph_enabled_ && !graph_failed_ && !prof_.enabled && c.do_cm >= 0 && p->n_steps >= 4 &&
@@ -1405,6 +1475,8 @@ class Engine : public EngineBase {
     std::vector<int> layer_start_;       // slot index of the first atom of every cell layer (ncz + 1)
     std::vector<DecompSeg> halo_send_, halo_recv_;
     DevBuf d_layer_start_, d_mom_;
+    int64_t sp_n_[3] = {0, 0, 0};
+    DevBuf d_sp_idx_k_[3], d_sp_par_k_[3], d_sp_partial_, d_sp_energy_;
     DevBuf d_mass_in_, d_charge_in_, d_ljp_in_;
     DevBuf d_pos4_, d_vel4_, d_f4_, d_xref4_, d_lj2_, d_orig_, d_inv_orig_, d_mass_;
     DevBuf d_pos4_t_, d_vel4_t_, d_lj2_t_, d_orig_t_, d_mass_t_;
@@ -1488,16 +1560,24 @@ int mb_set_neighbor_policy(mb_ctx* ctx, double r_list, int rebuild_every) {
 int mb_forces(mb_ctx* ctx, const void* coords, void* fs_mat, void* virial, int64_t step_n) {
     MB_CTX_GUARD(ctx);
     if (!fs_mat) return mb::set_error(MB_ERR_INVALID, "fs_mat is null");
-    return ctx->e->forces_energy(coords, fs_mat, nullptr, virial, step_n);
+    return ctx->e->forces_energy(coords, fs_mat, nullptr, virial, step_n, false);
 }
 int mb_energy(mb_ctx* ctx, const void* coords, void* pe, int64_t step_n) {
     MB_CTX_GUARD(ctx);
     if (!pe) return mb::set_error(MB_ERR_INVALID, "pe is null");
-    return ctx->e->forces_energy(coords, nullptr, pe, nullptr, step_n);
+    return ctx->e->forces_energy(coords, nullptr, pe, nullptr, step_n, false);
 }
 int mb_forces_energy(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, void* virial, int64_t step_n) {
     MB_CTX_GUARD(ctx);
-    return ctx->e->forces_energy(coords, fs_mat, pe, virial, step_n);
+    return ctx->e->forces_energy(coords, fs_mat, pe, virial, step_n, false);
+}
+int mb_forces_energy_all(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, int64_t step_n) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->forces_energy(coords, fs_mat, pe, nullptr, step_n, true);
+}
+int mb_set_specific(mb_ctx* ctx, int kind, int64_t n_terms, const int32_t* atom_idx, const double* params) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->set_specific(kind, n_terms, atom_idx, params);
 }
 int mb_simulate_vv(mb_ctx* ctx, void* coords, void* vels, const mb_vv_params_t* p) { MB_CTX_GUARD(ctx); return ctx->e->simulate_vv(coords, vels, p); }
 int mb_remove_cm_motion(mb_ctx* ctx, void* vels) { MB_CTX_GUARD(ctx); return ctx->e->remove_cm(vels); }

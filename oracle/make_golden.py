@@ -32,10 +32,11 @@ def main():
         lj14scale=np.float64(ff.lj14scale), coulomb14scale=np.float64(ff.coulomb14scale),
         velocities_300K=np.loadtxt(f"{REF}/openmm_6mrr/velocities_300K.txt"),
     )
-    for name in ("lj_only", "coul_only"):
+    for key in ("bond_idx", "bond_par", "angle_idx", "angle_par", "proper_idx", "proper_par", "improper_idx", "improper_par"):
+        out[key] = top[key]
+    for name in ("lj_only", "coul_only", "bond_only", "angle_only", "proptor_only", "improptor_only", "all_cut"):
         out[f"forces_{name}"] = np.loadtxt(f"{amber}/forces_{name}.txt")
         out[f"energy_{name}"] = np.float64(open(f"{amber}/energy_{name}.txt").read())
-    out["energy_all_cut"] = np.float64(open(f"{amber}/energy_all_cut.txt").read())
     np.savez_compressed(os.path.join(OUT, "6mrr.npz"), **out)
     print("wrote", os.path.join(OUT, "6mrr.npz"), os.path.getsize(os.path.join(OUT, "6mrr.npz")) / 1e6, "MB")
 

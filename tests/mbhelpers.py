@@ -115,3 +115,85 @@ def make_system(sysd, inters, dtype, r_list=0.0, n_steps=0):
                                   special_pairs=sysd.get("special", np.zeros((0, 2), np.int32)) + 1, n_steps=n_steps)
     return mb.System(atoms=atoms, coords=sysd["coords"].astype(dtype), boundary=mb.CubicBoundary(*sysd["box"]),
                      velocities=sysd["velocities"].astype(dtype), pairwise_inters=inters, neighbor_finder=nf, dtype=dtype)
+
+
+# ---------------------------------------------------------------------------------------------------
+# 6mrr (BASELINE config 3): full system from the golden fixture
+# ---------------------------------------------------------------------------------------------------
+def sixmrr_description(g):
+    box = g["box"]
+    x = g["coords"] - np.floor(g["coords"] / box) * box
+    return dict(n=len(x), box=box, coords=x, velocities=g["velocities_300K"], mass=g["mass"], charge=g["charge"],
+                sigma=g["sigma"], eps=g["eps"], excluded=g["excluded"], special=g["special"])
+
+
+def sixmrr_specific_lists(g):
+    import mollyb200 as mb
+    b, a = g["bond_idx"] + 1, g["angle_idx"] + 1
+    t = np.concatenate([g["proper_idx"], g["improper_idx"]]) + 1
+    tp = np.concatenate([g["proper_par"], g["improper_par"]])
+    return (mb.InteractionList2Atoms(b[:, 0], b[:, 1], g["bond_par"][:, 0], g["bond_par"][:, 1]),
+            mb.InteractionList3Atoms(a[:, 0], a[:, 1], a[:, 2], g["angle_par"][:, 0], g["angle_par"][:, 1]),
+            mb.InteractionList4Atoms(t[:, 0], t[:, 1], t[:, 2], t[:, 3], tp[:, 0], tp[:, 1], tp[:, 2]))
+
+
+def sixmrr_system(g, dtype, r_list=1.2, n_steps=0, bonded=True, coords=None, velocities=None, device=0):
+    """System(6mrr_equil.pdb, ff99SBildn + tip3p; nonbonded_method=:cutoff) as benchmark/protein.jl:24-37 builds it:
+    LJ(rc 1.0, w14 0.5) + CoulombReactionField(rc 1.0, eps 78.3, w14 0.8333) + bonds/angles/torsions."""
+    import mollyb200 as mb
+    sd = sixmrr_description(g)
+    atoms = mb.atoms_from_arrays(sd["mass"], sd["charge"], sd["sigma"], sd["eps"], dtype)
+    inters = (mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True, weight_special=float(g["lj14scale"])),
+              mb.CoulombReactionField(dist_cutoff=1.0, use_neighbors=True, weight_special=float(g["coulomb14scale"])))
+    nf = mb.GPUNeighborFinder(dist_cutoff=r_list, excluded_pairs=g["excluded"] + 1, special_pairs=g["special"] + 1, n_steps=n_steps)
+    x = sd["coords"] if coords is None else coords
+    v = sd["velocities"] if velocities is None else velocities
+    return mb.System(atoms=atoms, coords=np.asarray(x).astype(dtype), boundary=mb.CubicBoundary(*sd["box"]),
+                     velocities=np.asarray(v).astype(dtype), pairwise_inters=inters, neighbor_finder=nf, dtype=dtype,
+                     specific_inter_lists=sixmrr_specific_lists(g) if bonded else (), device=device)
+
+
+def sixmrr_oracle(g, dtype=np.float64):
+    from oracle import oracle as o
+    sd = sixmrr_description(g)
+    inters = [o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=float(g["lj14scale"]), use_neighbors=True),
+              o.Inter(o.CRF, o.CUT_DISTANCE, 1.0, weight_special=float(g["coulomb14scale"]), use_neighbors=True)]
+    return make_oracle(sd, inters, dtype=dtype), sd
+
+
+def bonded_forces_oracle(g, x):
+    from oracle import bonded as bd
+    box = g["box"]
+    f = np.zeros_like(x, dtype=np.float64)
+    e = 0.0
+    for fn, idx, par in ((bd.bond_forces, "bond_idx", "bond_par"), (bd.angle_forces, "angle_idx", "angle_par"),
+                         (bd.torsion_forces, "proper_idx", "proper_par"), (bd.torsion_forces, "improper_idx", "improper_par")):
+        ff, ee = fn(np.asarray(x, np.float64), box, g[idx], g[par])
+        f += ff
+        e += ee
+    return f, e
+
+
+def oracle_vv_with_bonded(g, x, v, dt, n_steps, r_list=1.2, nl_every=10):
+    """VelocityVerlet simulate! (src/simulators.jl:547-668) with pairwise (C oracle, neighbour list) + bonded (numpy)
+    forces, f64, remove_CM_motion = 1."""
+    orc, sd = sixmrr_oracle(g)
+    box, m = sd["box"], sd["mass"]
+    x = x - np.floor(x / box) * box
+    v = orc.remove_cm(v)
+
+    def forces(xx, nl):
+        f, _, _ = orc.forces_nl(xx, nl, energy=False)
+        return f + bonded_forces_oracle(g, xx)[0]
+    nl = orc.neighbor_list(x, r_list)
+    f = forces(x, nl)
+    for step in range(1, n_steps + 1):
+        v = v + f / m[:, None] * (dt / 2)
+        x = x + v * dt
+        x = x - np.floor(x / box) * box
+        f = forces(x, nl)
+        v = v + f / m[:, None] * (dt / 2)
+        v = orc.remove_cm(v)
+        if step % nl_every == 0:
+            nl = orc.neighbor_list(x, r_list)
+    return x, v

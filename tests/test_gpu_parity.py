@@ -270,6 +270,67 @@ def test_forces_track_moving_coordinates_and_rebuild():
 
 
 # ---------------------------------------------------------------------------------------------------
+# bonded terms + the whole 6mrr :cutoff system
+# ---------------------------------------------------------------------------------------------------
+def test_6mrr_all_cut_openmm_golden_f64(golden_6mrr):
+    """LJ + CRF + HarmonicBond + HarmonicAngle + PeriodicTorsion (propers + impropers) on the GPU vs OpenMM's
+    forces_all_cut / energy_all_cut (test/protein.jl:263-275: 1e-7 kJ/mol/nm, 1e-5 kJ/mol)."""
+    g = golden_6mrr
+    s = H.sixmrr_system(g, np.float64, r_list=1.2)
+    f, e = mb.forces_energy(s)
+    e += o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
+    err = np.linalg.norm(f - g["forces_all_cut"], axis=1).max()
+    print(f"[6mrr all_cut f64] max|dF|={err:.3e} dE={e - float(g['energy_all_cut']):.3e}")
+    assert err < 1e-7
+    assert abs(e - float(g["energy_all_cut"])) < 1e-5
+    # bonded-only parity: pairwise-only call subtracted
+    f_pair = mb.forces(s)
+    fb_ref = sum(g[f"forces_{k}_only"] for k in ("bond", "angle", "proptor", "improptor"))
+    assert np.linalg.norm((f - f_pair) - fb_ref, axis=1).max() < 1e-7
+    s.close()
+
+
+def test_6mrr_all_cut_f32_vs_oracle(golden_6mrr):
+    g = golden_6mrr
+    s = H.sixmrr_system(g, np.float32, r_list=1.15)
+    orc, sd = H.sixmrr_oracle(g)
+    x32 = sd["coords"].astype(np.float32)
+    f_ref, _, _ = orc.forces_allpairs(x32.astype(np.float64), energy=False)
+    fb, eb = H.bonded_forces_oracle(g, x32.astype(np.float64))
+    f, e = mb.forces_energy(s)
+    fb_gpu = f - mb.forces(s)
+    berr = np.abs(fb_gpu - fb).max()
+    print(f"[6mrr bonded f32] max|dF_bonded|={berr:.3e} (max|F_bonded|={np.abs(fb).max():.3e})")
+    assert berr < 2e-5 * np.abs(fb).max() + 5e-2  # stiff bonds: (r - r0) cancellation in f32
+    s.close()
+
+
+def test_6mrr_vv_with_bonded_f64_matches_oracle(golden_6mrr):
+    """The benchmark/protein.jl system (dt 0.5 fs, no coupling) for 20 steps vs the oracle's VV loop."""
+    g = golden_6mrr
+    s = H.sixmrr_system(g, np.float64, r_list=1.2, n_steps=10)
+    sd = H.sixmrr_description(g)
+    x_ref, v_ref = H.oracle_vv_with_bonded(g, sd["coords"], sd["velocities"], 0.0005, 20, r_list=1.2, nl_every=10)
+    mb.simulate(s, mb.VelocityVerlet(dt=0.0005), 20)
+    ex, ev = _pos_err(s.coords, x_ref, sd["box"]), np.abs(s.velocities - v_ref).max()
+    print(f"[6mrr VV bonded f64] dx={ex:.3e} dv={ev:.3e} graph={s.stats()['graph_mode']}")
+    assert ex < 1e-9 and ev < 1e-6
+    s.close()
+
+
+def test_6mrr_dynamics_f32_stable(golden_6mrr):
+    """500 steps of the full system in f32 with the Andersen thermostat (config 3): temperature stays physical."""
+    g = golden_6mrr
+    s = H.sixmrr_system(g, np.float32, r_list=1.12)
+    sim = mb.VelocityVerlet(dt=0.0005, coupling=mb.AndersenThermostat(300.0, 1.0))
+    mb.simulate(s, sim, 500, rng=np.random.default_rng(3))
+    t = mb.temperature(s)
+    print(f"[6mrr f32 500 steps] T={t:.1f} K rebuilds={s.stats()['n_rebuilds']}")
+    assert 250.0 < t < 400.0 and np.isfinite(s.coords).all()
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------
 # VelocityVerlet
 # ---------------------------------------------------------------------------------------------------
 def _pos_err(a, b, box):

@@ -157,3 +157,27 @@ def test_vv_oracle_conserves_energy_and_momentum():
     d = x2.astype(np.float64) - x3
     d -= sd["box"] * np.round(d / sd["box"])
     assert np.abs(d).max() < 1e-4
+
+
+@pytest.mark.parametrize("name,idx,par", [("bond_only", "bond_idx", "bond_par"), ("angle_only", "angle_idx", "angle_par"),
+                                          ("proptor_only", "proper_idx", "proper_par"),
+                                          ("improptor_only", "improper_idx", "improper_par")])
+def test_6mrr_bonded_openmm_golden(golden_6mrr, name, idx, par):
+    # test/protein.jl:206-276: bonded terms vs OpenMM (energies 164735.97 / 2839.82 / 2892.48 / 128.24 kJ/mol)
+    from oracle import bonded as bd
+    g = golden_6mrr
+    fn = {"bond_only": bd.bond_forces, "angle_only": bd.angle_forces}.get(name, bd.torsion_forces)
+    f, e = fn(g["coords"], g["box"], g[idx], g[par])
+    assert np.linalg.norm(f - g[f"forces_{name}"], axis=1).max() < 1e-7
+    assert abs(e - float(g[f"energy_{name}"])) < 1e-5
+
+
+def test_6mrr_all_cut_openmm_golden(golden_6mrr):
+    # the whole :cutoff system: LJ + CRF + bonded (+ LJ dispersion correction in the energy), E = 41763.84577241427
+    g = golden_6mrr
+    orc, sd = H.sixmrr_oracle(g)
+    f, e, _ = orc.forces_allpairs(sd["coords"])
+    fb, eb = H.bonded_forces_oracle(g, sd["coords"])
+    e += eb + o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
+    assert np.linalg.norm(f + fb - g["forces_all_cut"], axis=1).max() < 1e-7
+    assert abs(e - float(g["energy_all_cut"])) < 1e-5
