@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "tests"), ROOT):
     sys.path.insert(0, p)
 import bench  # noqa: E402
+import mbhelpers as H  # noqa: E402
 import mollyb200 as mb  # noqa: E402
 
 
@@ -31,8 +32,10 @@ def main():
             bx, by, bz, lanes = [int(v) for v in cfg.split(",")]
             nf = mb.GPUNeighborFinder(dist_cutoff=r_list, excluded_pairs=sd.get("excluded", np.zeros((0, 2), np.int32)) + 1,
                                       special_pairs=sd.get("special", np.zeros((0, 2), np.int32)) + 1, n_steps=0)
+            specific = H.sixmrr_specific_lists(sd["golden"]) if "golden" in sd else ()
             s = mb.System(atoms=atoms, coords=sd["coords"].copy(), boundary=mb.CubicBoundary(*sd["box"]),
-                          velocities=sd["velocities"].copy(), pairwise_inters=inters, neighbor_finder=nf, dtype=np.float32)
+                          velocities=sd["velocities"].copy(), pairwise_inters=inters, neighbor_finder=nf, dtype=np.float32,
+                          specific_inter_lists=specific)
             s.engine()
             try:
                 s.set_launch_config((bx, by, bz), lanes)

