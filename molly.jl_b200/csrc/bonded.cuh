@@ -67,11 +67,9 @@ __device__ __forceinline__ void block_energy(double e, double* __restrict__ part
 
 // slot_of: original atom index -> slot (inv_orig), or nullptr when positions are in original order
 template <typename T, bool ENERGY>
-__global__ void __launch_bounds__(BONDED_THREADS)
-    bond_kernel(int n, const int* __restrict__ idx, const T* __restrict__ par, const int* __restrict__ slot_of,
-                const typename VT<T>::T4* __restrict__ pos4, typename VT<T>::T4* __restrict__ f4, BoxT box,
-                double* __restrict__ partial) {
-    const int t = blockIdx.x * BONDED_THREADS + threadIdx.x;
+__device__ __forceinline__ double bond_term(int t, int n, const int* __restrict__ idx, const T* __restrict__ par,
+                                            const int* __restrict__ slot_of, const typename VT<T>::T4* __restrict__ pos4,
+                                            typename VT<T>::T4* __restrict__ f4, const BoxT& box) {
     double e = 0;
     if (t < n) {
         const T L[3] = {(T)box.L[0], (T)box.L[1], (T)box.L[2]};
@@ -87,15 +85,13 @@ __global__ void __launch_bounds__(BONDED_THREADS)
         add_force<T>(f4, j, -fi);
         if (ENERGY) e = 0.5 * (double)k * (double)(r - r0) * (double)(r - r0);
     }
-    if (ENERGY) block_energy<T>(e, partial);
+    return e;
 }
 
 template <typename T, bool ENERGY>
-__global__ void __launch_bounds__(BONDED_THREADS)
-    angle_kernel(int n, const int* __restrict__ idx, const T* __restrict__ par, const int* __restrict__ slot_of,
-                 const typename VT<T>::T4* __restrict__ pos4, typename VT<T>::T4* __restrict__ f4, BoxT box,
-                 double* __restrict__ partial) {
-    const int t = blockIdx.x * BONDED_THREADS + threadIdx.x;
+__device__ __forceinline__ double angle_term(int t, int n, const int* __restrict__ idx, const T* __restrict__ par,
+                                             const int* __restrict__ slot_of, const typename VT<T>::T4* __restrict__ pos4,
+                                             typename VT<T>::T4* __restrict__ f4, const BoxT& box) {
     double e = 0;
     if (t < n) {
         const T L[3] = {(T)box.L[0], (T)box.L[1], (T)box.L[2]};
@@ -123,16 +119,14 @@ __global__ void __launch_bounds__(BONDED_THREADS)
             if (ENERGY) e = 0.5 * (double)k * (double)(th - th0) * (double)(th - th0);
         }
     }
-    if (ENERGY) block_energy<T>(e, partial);
+    return e;
 }
 
 // one (periodicity, phase, k) term per entry; a torsion with several terms appears several times
 template <typename T, bool ENERGY>
-__global__ void __launch_bounds__(BONDED_THREADS)
-    torsion_kernel(int n, const int* __restrict__ idx, const T* __restrict__ par, const int* __restrict__ slot_of,
-                   const typename VT<T>::T4* __restrict__ pos4, typename VT<T>::T4* __restrict__ f4, BoxT box,
-                   double* __restrict__ partial) {
-    const int t = blockIdx.x * BONDED_THREADS + threadIdx.x;
+__device__ __forceinline__ double torsion_term(int t, int n, const int* __restrict__ idx, const T* __restrict__ par,
+                                               const int* __restrict__ slot_of, const typename VT<T>::T4* __restrict__ pos4,
+                                               typename VT<T>::T4* __restrict__ f4, const BoxT& box) {
     double e = 0;
     if (t < n) {
         const T L[3] = {(T)box.L[0], (T)box.L[1], (T)box.L[2]};
@@ -160,6 +154,31 @@ __global__ void __launch_bounds__(BONDED_THREADS)
             add_force<T>(f4, l, fl);
             if (ENERGY) e = (double)kk * (1.0 + cos((double)ang));
         }
+    }
+    return e;
+}
+
+// All specific interactions in one launch: CTAs [0, nb0) bonds, [nb0, nb0+nb1) angles, the rest torsions.
+struct BondedLists {
+    int n[3];
+    int nblk[3];
+    const int* idx[3];
+    const void* par[3];
+};
+template <typename T, bool ENERGY>
+__global__ void __launch_bounds__(BONDED_THREADS)
+    bonded_kernel(BondedLists L, const int* __restrict__ slot_of, const typename VT<T>::T4* __restrict__ pos4,
+                  typename VT<T>::T4* __restrict__ f4, BoxT box, double* __restrict__ partial) {
+    int blk = blockIdx.x;
+    double e = 0;
+    if (blk < L.nblk[0]) {
+        e = bond_term<T, ENERGY>(blk * BONDED_THREADS + threadIdx.x, L.n[0], L.idx[0], static_cast<const T*>(L.par[0]), slot_of, pos4, f4, box);
+    } else if (blk < L.nblk[0] + L.nblk[1]) {
+        blk -= L.nblk[0];
+        e = angle_term<T, ENERGY>(blk * BONDED_THREADS + threadIdx.x, L.n[1], L.idx[1], static_cast<const T*>(L.par[1]), slot_of, pos4, f4, box);
+    } else {
+        blk -= L.nblk[0] + L.nblk[1];
+        e = torsion_term<T, ENERGY>(blk * BONDED_THREADS + threadIdx.x, L.n[2], L.idx[2], static_cast<const T*>(L.par[2]), slot_of, pos4, f4, box);
     }
     if (ENERGY) block_energy<T>(e, partial);
 }

@@ -353,7 +353,7 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
 // Stages pos4 (and optionally lj2) runs of brick b into shared memory with bulk async copies, then
 // converts the positions to the brick-local frame (origin = brick corner, periodic image applied) in
 // double so that i-j differences carry no box-size rounding error.
-template <typename T, bool WITH_LJ>
+template <typename T, bool WITH_LJ, bool ALWAYS_LOCALIZE>
 __device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickHdr& hd, const Run* __restrict__ my_runs,
                                            const typename VT<T>::T4* __restrict__ pos4,
                                            const typename VT<T>::T2* __restrict__ lj2,
@@ -385,6 +385,12 @@ __device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickH
         }
     }
     mbar_wait(bar, 0);
+    // Bricks whose halo holds no periodic image keep global coordinates: the pair loop only uses differences of
+    // positions, which are exact in the same frame. Only bricks at the box boundary are re-centred.
+    if (!ALWAYS_LOCALIZE && !hd.any_shift) {
+        __syncthreads();
+        return;
+    }
     // brick-local frame
     int B[3] = {b % g.nb[0], (b / g.nb[0]) % g.nb[1], b / (g.nb[0] * g.nb[1])};
     double org[3];
@@ -443,7 +449,7 @@ __global__ void __launch_bounds__(256)
     for (int k = tid; k < g.n_irows; k += blockDim.x) s_rows[k] = irows[(size_t)b * g.n_irows + k];
     __syncthreads();
     fence_proxy_async();
-    stage_halo<T, false>(g, b, hd, my_runs, pos4, nullptr, s_pos, nullptr, &s_bar);
+    stage_halo<T, false, true>(g, b, hd, my_runs, pos4, nullptr, s_pos, nullptr, &s_bar);
     for (int r = wid; r < g.max_runs; r += nw) {
         Run run = my_runs[r];
         for (int k = lane; k < run.count; k += 32) s_orig[run.soff + k] = orig[run.gstart + k];

@@ -672,24 +672,21 @@ class Engine : public EngineBase {
             MB_CUDA(cudaMemsetAsync(d_sp_energy_.p, 0, sizeof(double), stream_));
         }
         double* part = d_sp_partial_.as<double>();
+        BondedLists L;
+        int total_blk = 0;
         for (int kind = 0; kind < 3; kind++) {
-            const int n = (int)sp_n_[kind];
-            if (n == 0) continue;
-            const int nblk = (n + BONDED_THREADS - 1) / BONDED_THREADS;
-            const int* idx = d_sp_idx_k_[kind].as<int>();
-            const T* par = d_sp_par_k_[kind].as<T>();
-#define MB_BONDED(KERN)                                                                                                  \
-    if (energy) KERN<T, true><<<nblk, BONDED_THREADS, 0, stream_>>>(n, idx, par, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part); \
-    else KERN<T, false><<<nblk, BONDED_THREADS, 0, stream_>>>(n, idx, par, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part)
-            if (kind == 0) { MB_BONDED(bond_kernel); }
-            else if (kind == 1) { MB_BONDED(angle_kernel); }
-            else { MB_BONDED(torsion_kernel); }
-#undef MB_BONDED
+            L.n[kind] = (int)sp_n_[kind];
+            L.nblk[kind] = (L.n[kind] + BONDED_THREADS - 1) / BONDED_THREADS;
+            L.idx[kind] = d_sp_idx_k_[kind].as<int>();
+            L.par[kind] = d_sp_par_k_[kind].p;
+            total_blk += L.nblk[kind];
+        }
+        if (energy) bonded_kernel<T, true><<<total_blk, BONDED_THREADS, 0, stream_>>>(L, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part);
+        else bonded_kernel<T, false><<<total_blk, BONDED_THREADS, 0, stream_>>>(L, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part);
+        launches_++;
+        if (energy) {
+            sum_partials_kernel<<<1, 256, 0, stream_>>>(total_blk, part, d_sp_energy_.as<double>());
             launches_++;
-            if (energy) {
-                sum_partials_kernel<<<1, 256, 0, stream_>>>(nblk, part, d_sp_energy_.as<double>());
-                launches_++;
-            }
         }
         MB_CUDA(cudaGetLastError());
         return MB_OK;
@@ -845,7 +842,7 @@ class Engine : public EngineBase {
             MB_TRY(enqueue_rebuild(false, true));
             Control c;
             MB_TRY(read_ctl(c));
-            int cap = (int)(c.max_halo * (1.0 + 0.15 * cap_scale_)) + 64;
+            int cap = (int)(c.max_halo * (1.0 + 0.08 * cap_scale_)) + 32;  // temporal drift of the fullest brick's halo
             cap = (cap + 63) & ~63;
             g_.halo_cap = std::min(cap, 65535);
             size_t need = std::max(force_smem_bytes() + 2048, build_smem_bytes() + 1024);
@@ -1105,16 +1102,15 @@ class Engine : public EngineBase {
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
         prof_.begin(Prof::VV);
-        vv_kick_drift_kernel<T><<<nb, 256, 0, stream_>>>(s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(),
-                                                         d_pos4_.as<T4>(), d_vel4_.as<T4>(), c.flag_ptr);
+        vv_kick_drift_kernel<T><<<std::min(nb, 4 * sm_count_), 256, 0, stream_>>>(
+            s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
+            c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0);
         prof_.end(Prof::VV);
         launches_++;
         if (clear_cm_after_k1) {
             clear_cm_kernel<T><<<1, 1, 0, stream_>>>(cm);
             launches_++;
         }
-        decide_kernel<<<1, 32, 0, stream_>>>(ctl, handle, capture && path_ == 1 ? 1 : 0);
-        launches_++;
         if (path_ == 0) {
             wrap_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_ap_, d_pos4_.as<T4>());
             launches_++;

@@ -22,6 +22,9 @@ constexpr int FORCE_THREADS = 256;
 #ifndef MB_LIST_BATCH
 #define MB_LIST_BATCH 8
 #endif
+#ifndef MB_USE_F32X2
+#define MB_USE_F32X2 0
+#endif
 #ifndef MB_MIN_BLOCKS
 #define MB_MIN_BLOCKS 4
 #endif
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
     __shared__ IRow s_rows[64];
     const Run* my_runs = runs + (size_t)b * g.max_runs;
     for (int k = tid; k < g.n_irows; k += blockDim.x) s_rows[k] = irows[(size_t)b * g.n_irows + k];
-    stage_halo<T, !UNIFORM>(g, b, hd, my_runs, pos4, lj2, s_pos, s_lj, &s_bar);
+    stage_halo<T, !UNIFORM, false>(g, b, hd, my_runs, pos4, lj2, s_pos, s_lj, &s_bar);
 
     constexpr int NSUB = FORCE_THREADS / LPA;
     const int sub = tid / LPA, l = tid % LPA;
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
         const T kq_i = P.ke * pi.w;
         const ushort2 cnt = valid ? counts[slot] : make_ushort2(0, 0);
         T fx = (T)0, fy = (T)0, fz = (T)0;
+        float2 axx = make_float2(0.f, 0.f), ayy = axx, azz = axx;  // packed-f32 accumulators (two neighbours per lane)
 
         auto eval = [&](int j, auto special_tag) {
             constexpr bool SPECIAL = decltype(special_tag)::value;
@@ -122,6 +126,30 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
                 pj[u] = s_pos[j[u]];
                 if (!UNIFORM) lj[u] = s_lj[j[u]];
             }
+#if MB_USE_F32X2
+            if constexpr (std::is_same<T, float>::value && UNIFORM && !SHIFT && !ENERGY && COUL == COUL_NONE) {
+                // Blackwell packed-f32 path (FADD2 / FMUL2 / FFMA2): two neighbours per instruction
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    const float4 a = pj[2 * h2], b = pj[2 * h2 + 1];
+                    const float2 one_m = make_float2(-1.f, -1.f);
+                    const float2 dx = __ffma2_rn(make_float2(a.x, b.x), one_m, make_float2(pi.x, pi.x));
+                    const float2 dy = __ffma2_rn(make_float2(a.y, b.y), one_m, make_float2(pi.y, pi.y));
+                    const float2 dz = __ffma2_rn(make_float2(a.z, b.z), one_m, make_float2(pi.z, pi.z));
+                    const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                    const float2 iv = make_float2(frcp(r2.x), frcp(r2.y));
+                    const float2 i3 = __fmul2_rn(__fmul2_rn(iv, iv), iv);
+                    const float2 tt = __ffma2_rn(make_float2(P.uni_A, P.uni_A), i3, make_float2(-P.uni_B, -P.uni_B));
+                    float2 fr = __fmul2_rn(tt, __fmul2_rn(i3, iv));
+                    fr.x = (r2.x <= P.lj_rc2) ? fr.x : 0.f;
+                    fr.y = (r2.y <= P.lj_rc2) ? fr.y : 0.f;
+                    axx = __ffma2_rn(fr, dx, axx);
+                    ayy = __ffma2_rn(fr, dy, ayy);
+                    azz = __ffma2_rn(fr, dz, azz);
+                }
+                return;
+            }
+#endif
             T dx[4], dy[4], dz[4], r2[4], fr[4], e[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -176,6 +204,13 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
         }
         // special (1-4) pairs
         for (int m = l; m < (int)cnt.y; m += LPA) eval((int)slist[(size_t)slot * g.sstride + m], std::true_type{});
+#if MB_USE_F32X2
+        if constexpr (std::is_same<T, float>::value) {
+            fx += axx.x + axx.y;
+            fy += ayy.x + ayy.y;
+            fz += azz.x + azz.y;
+        }
+#endif
         // reduce the LPA partial forces
         __syncwarp();
 #pragma unroll

@@ -127,38 +127,50 @@ __global__ void scatter_forces_kernel(int n, const typename VT<T>::T4* __restric
     fs_mat[3 * (size_t)o + 2] += f.z;
 }
 
-// ---- K1: first half kick + drift + displacement check ------------------------------------------
+// ---- K1: first half kick + drift + displacement check; the last CTA to finish does the step bookkeeping:
+// advance step_n, apply the fixed-interval neighbour policy (find_neighbors every n_steps, src/neighbors.jl:671) and
+// publish the rebuild decision to the CUDA graph's conditional node (when the step runs as a graph).
 template <typename T>
 __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half2, const CmState<T>* __restrict__ cm,
                                      const typename VT<T>::T4* __restrict__ f4,
                                      const typename VT<T>::T4* __restrict__ xref4, typename VT<T>::T4* __restrict__ pos4,
-                                     typename VT<T>::T4* __restrict__ vel4, int* __restrict__ flag) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    s += s0;  // [s0, s0 + n): the slots this rank owns
-    typename VT<T>::T4 v = vel4[s];
-    const typename VT<T>::T4 f = f4[s];
-    typename VT<T>::T4 p = pos4[s];
-    const typename VT<T>::T4 r = xref4[s];
-    if (cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
-    const T a = v.w * dt_half;  // (1/m) dt/2
-    v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
-    p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
-    vel4[s] = v;
-    pos4[s] = p;
-    const T dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
-    if (dx * dx + dy * dy + dz * dz > skin_half2) *flag = 1;
-}
-
-// ---- step bookkeeping on the device: advance step_n, apply the fixed-interval neighbour policy
-// (find_neighbors every n_steps, src/neighbors.jl:671) and publish the rebuild decision to the CUDA
-// graph's conditional node (when the step runs as a graph).
-__global__ void decide_kernel(Control* ctl, cudaGraphConditionalHandle handle, int use_handle) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const long long step_n = ++ctl->step;
-    const long long k = step_n - ctl->init_step;
-    if (ctl->rebuild_every > 0 && k > 1 && (step_n - 1) % ctl->rebuild_every == 0) ctl->rebuild = 1;
-    if (use_handle) cudaGraphSetConditional(handle, ctl->rebuild ? 1u : 0u);
+                                     typename VT<T>::T4* __restrict__ vel4, int* __restrict__ flag, Control* __restrict__ ctl,
+                                     cudaGraphConditionalHandle handle, int use_handle) {
+    const bool cmv = cm->valid != 0;
+    const T cx = cm->v[0], cy = cm->v[1], cz = cm->v[2];
+    bool moved = false;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int s = s0 + k;  // [s0, s0 + n): the slots this rank owns
+        typename VT<T>::T4 v = vel4[s];
+        const typename VT<T>::T4 f = f4[s];
+        typename VT<T>::T4 p = pos4[s];
+        const typename VT<T>::T4 r = xref4[s];
+        if (cmv) { v.x -= cx; v.y -= cy; v.z -= cz; }
+        const T a = v.w * dt_half;  // (1/m) dt/2
+        v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
+        p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
+        vel4[s] = v;
+        pos4[s] = p;
+        const T dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
+        moved |= (dx * dx + dy * dy + dz * dz > skin_half2);
+    }
+    if (moved) *flag = 1;
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicInc(&ctl->ticket, gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const long long step_n = ++ctl->step;
+        const long long kk = step_n - ctl->init_step;
+        int rb = *(volatile int*)&ctl->rebuild;
+        if (ctl->rebuild_every > 0 && kk > 1 && (step_n - 1) % ctl->rebuild_every == 0) { rb = 1; ctl->rebuild = 1; }
+        if (use_handle) cudaGraphSetConditional(handle, rb ? 1u : 0u);
+    }
 }
 
 // ---- K2: second half kick + centre-of-mass momentum -------------------------------------------
