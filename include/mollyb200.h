@@ -82,7 +82,7 @@ typedef struct {
     int64_t force_launches, vv_launches, rebuild_launches;
     int32_t graph_mode;        /* last mb_simulate_vv: 1 = CUDA-graph step with conditional rebuild node,
                                 * 0 = stream launches, -1 = graph construction failed (stream launches) */
-    int32_t reserved_;
+    int32_t reserved_;         /* decomposed runs: the rebuild interval the next call will use (adapted from displacements) */
 } mb_stats_t;
 
 const char* mb_last_error(void);

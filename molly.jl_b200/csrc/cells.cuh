@@ -34,6 +34,9 @@ struct Control {
     long long step;       // MD step counter (simulate!'s step_n), advanced on the device
     long long init_step;  // step_n at the start of the current mb_simulate_vv call
     unsigned int rng[4];  // Andersen thermostat: ctr1 lo/hi, key lo/hi
+    // displacement bookkeeping (float bits of squared distances, non-negative floats order like unsigned ints)
+    unsigned int max_disp2_bits;       // largest |x - x_ref|^2 since the last rebuild
+    unsigned int call_max_disp2_bits;  // largest value any rebuild interval of the current call reached
 };
 
 struct BrickHdr {
@@ -589,6 +592,8 @@ __global__ void rebuild_finish_kernel(Control* ctl) {
         ctl->disp = 0;
         ctl->rebuild = 0;
         ctl->n_rebuilds++;
+        if (ctl->max_disp2_bits > ctl->call_max_disp2_bits) ctl->call_max_disp2_bits = ctl->max_disp2_bits;
+        ctl->max_disp2_bits = 0;
     }
 }
 __global__ void rebuild_begin_kernel(Control* ctl) {

@@ -714,6 +714,29 @@ class Engine : public EngineBase {
         decomp_plan(ncz, g_.h, nranks_, rank_, layer_start_.data(), halo_send_, halo_recv_);
         return MB_OK;
     }
+    // Decomposed runs rebuild at a fixed interval (every rank must take the same branch without a host round trip).
+    // The interval for the NEXT call is derived from the largest displacement any interval of this call reached:
+    // n_next = 0.8 * n * (skin/2) / d_max, agreed between ranks with one max-all-reduce. Violations are still counted.
+    int adapt_interval() {
+        unsigned int* bits = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ctl_.p) + offsetof(Control, max_disp2_bits));
+        // the running interval counts too: take max(max_disp2_bits, call_max_disp2_bits) on the device side by reading both
+        unsigned int h[2];
+        MB_CUDA(cudaMemcpyAsync(h, bits, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        float d2;
+        unsigned int mx = std::max(h[0], h[1]);
+        memcpy(&d2, &mx, sizeof(float));
+        float* dbuf = reinterpret_cast<float*>(d_mom_.as<double>() + 7);
+        MB_CUDA(cudaMemcpyAsync(dbuf, &d2, sizeof(float), cudaMemcpyHostToDevice, stream_));
+        MB_NCCL(g_nccl.AllReduce(dbuf, dbuf, 1, (ncclDataType_t)7 /* ncclFloat32 */, (ncclRedOp_t)2 /* ncclMax */, comm_, stream_));
+        MB_CUDA(cudaMemcpyAsync(&d2, dbuf, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        if (d2 > 0.f && skin_ > 0) {
+            double n_next = 0.8 * auto_every_ * (0.5 * skin_) / std::sqrt((double)d2);
+            auto_every_ = (int)std::min(400.0, std::max(5.0, std::floor(n_next)));
+        }
+        return MB_OK;
+    }
     // forward halo exchange of positions (x, y, z, q as 16/32-byte records): grouped NCCL send/recv between slabs
     int halo_exchange() {
         MB_NCCL(g_nccl.GroupStart());
@@ -1275,13 +1298,15 @@ class Engine : public EngineBase {
         }
         // step bookkeeping lives on the device (tail of Control)
         {
-            struct Tail { int rebuild_every; long long step, init_step; unsigned int rng[4]; } t;
+            struct Tail { int rebuild_every; long long step, init_step; unsigned int rng[4]; unsigned int max_disp2_bits, call_max_disp2_bits; } t;
             static_assert(sizeof(Tail) == sizeof(Control) - offsetof(Control, rebuild_every), "Control tail layout");
-            t.rebuild_every = (decomposed() && path_ == 1 && rebuild_every_ == 0) ? 20 : rebuild_every_;
+            t.rebuild_every = (decomposed() && path_ == 1 && rebuild_every_ == 0) ? auto_every_ : rebuild_every_;
             t.step = p->init_step;
             t.init_step = p->init_step;
             t.rng[0] = (unsigned int)p->rng_ctr1; t.rng[1] = (unsigned int)(p->rng_ctr1 >> 32);
             t.rng[2] = (unsigned int)p->rng_key; t.rng[3] = (unsigned int)(p->rng_key >> 32);
+            t.max_disp2_bits = 0;
+            t.call_max_disp2_bits = 0;
             MB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(ctl) + offsetof(Control, rebuild_every), &t, sizeof(t),
                                     cudaMemcpyHostToDevice, stream_));
             MB_CUDA(cudaStreamSynchronize(stream_));  // t is a local
@@ -1327,7 +1352,7 @@ class Engine : public EngineBase {
                 const int64_t step_n = p->init_step + k;
                 const int do_cm = (p->remove_cm_every != 0 && step_n % p->remove_cm_every == 0) ? 1 : 0;
                 const bool clear_after_k1 = cm_pending && !do_cm;  // K1 consumed v_cm; nothing overwrites it this step
-                const int every = (dec && rebuild_every_ == 0) ? 20 : rebuild_every_;  // decomposed runs use a fixed interval
+                const int every = (dec && rebuild_every_ == 0) ? auto_every_ : rebuild_every_;  // decomposed: fixed interval, adapted per call
                 const bool hint = every > 0 && k > 1 && (step_n - 1) % every == 0;
                 MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint));
                 cm_pending = (do_cm != 0) && !c.thermostat;
@@ -1337,6 +1362,7 @@ class Engine : public EngineBase {
         if (dec) {
             MB_TRY(allgather_state());  // every rank returns the whole system
             build_nb_ = -1;
+            if (rebuild_every_ == 0) MB_TRY(adapt_interval());
         }
         // export
         T* xo = c_dev ? reinterpret_cast<T*>(coords) : d_stage_a_.as<T>();
@@ -1412,6 +1438,7 @@ class Engine : public EngineBase {
         o->r_list = r_list_;
         o->kernel_launches = launches_;
         o->graph_mode = graph_used_ ? 1 : (graph_failed_ ? -1 : 0);
+        o->reserved_ = decomposed() ? auto_every_ : 0;
         prof_.collect();
         o->force_ms = prof_.ms[Prof::FORCE]; o->force_launches = prof_.count[Prof::FORCE];
         o->vv_ms = prof_.ms[Prof::VV]; o->vv_launches = prof_.count[Prof::VV];
@@ -1468,6 +1495,7 @@ class Engine : public EngineBase {
     int own_b0_ = 0, own_nb_ = 0;        // this rank's bricks (static for a geometry)
     int build_b0_ = 0, build_nb_ = -1;   // brick range the list builder covers (-1 = all)
     int own_s0_ = 0, own_n_ = 0;         // this rank's slots (changes at every rebuild)
+    int auto_every_ = 20;                // rebuild interval of decomposed runs when the policy is displacement-triggered
     std::vector<int> layer_start_;       // slot index of the first atom of every cell layer (ncz + 1)
     std::vector<DecompSeg> halo_send_, halo_recv_;
     DevBuf d_layer_start_, d_mom_;

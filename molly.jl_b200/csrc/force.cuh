@@ -23,7 +23,7 @@ constexpr int FORCE_THREADS = 256;
 #define MB_LIST_BATCH 8
 #endif
 #ifndef MB_USE_F32X2
-#define MB_USE_F32X2 0
+#define MB_USE_F32X2 1  // Blackwell packed-f32 (FFMA2/FMUL2) pair loop for the uniform-LJ f32 force path
 #endif
 #ifndef MB_MIN_BLOCKS
 #define MB_MIN_BLOCKS 4
@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
         const T kq_i = P.ke * pi.w;
         const ushort2 cnt = valid ? counts[slot] : make_ushort2(0, 0);
         T fx = (T)0, fy = (T)0, fz = (T)0;
+#if MB_USE_F32X2
         float2 axx = make_float2(0.f, 0.f), ayy = axx, azz = axx;  // packed-f32 accumulators (two neighbours per lane)
+        (void)axx; (void)ayy; (void)azz;
+#endif
 
         auto eval = [&](int j, auto special_tag) {
             constexpr bool SPECIAL = decltype(special_tag)::value;

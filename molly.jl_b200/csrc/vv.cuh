@@ -139,6 +139,7 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
     const bool cmv = cm->valid != 0;
     const T cx = cm->v[0], cy = cm->v[1], cz = cm->v[2];
     bool moved = false;
+    float d2max = 0.f;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int s = s0 + k;  // [s0, s0 + n): the slots this rank owns
         typename VT<T>::T4 v = vel4[s];
@@ -152,9 +153,13 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
         vel4[s] = v;
         pos4[s] = p;
         const T dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
-        moved |= (dx * dx + dy * dy + dz * dz > skin_half2);
+        const T d2 = dx * dx + dy * dy + dz * dz;
+        moved |= (d2 > skin_half2);
+        d2max = fmaxf(d2max, (float)d2);
     }
     if (moved) *flag = 1;
+    for (int o = 16; o > 0; o >>= 1) d2max = fmaxf(d2max, __shfl_xor_sync(0xffffffffu, d2max, o));
+    if ((threadIdx.x & 31) == 0 && d2max > 0.f) atomicMax(&ctl->max_disp2_bits, __float_as_uint(d2max));
     __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
