@@ -159,10 +159,14 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
     }
     if (moved) *flag = 1;
     for (int o = 16; o > 0; o >>= 1) d2max = fmaxf(d2max, __shfl_xor_sync(0xffffffffu, d2max, o));
-    if ((threadIdx.x & 31) == 0 && d2max > 0.f) atomicMax(&ctl->max_disp2_bits, __float_as_uint(d2max));
+    __shared__ float s_d2[32];
     __shared__ bool s_last;
+    if ((threadIdx.x & 31) == 0) s_d2[threadIdx.x >> 5] = d2max;
     __syncthreads();
     if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s_d2[w]);
+        if (m > 0.f) atomicMax(&ctl->max_disp2_bits, __float_as_uint(m));  // one atomic per CTA
         __threadfence();
         unsigned int t = atomicInc(&ctl->ticket, gridDim.x - 1);
         s_last = (t == gridDim.x - 1);
