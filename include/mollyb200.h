@@ -82,6 +82,8 @@ typedef struct {
     int64_t force_launches, vv_launches, rebuild_launches;
     int32_t graph_mode;        /* last mb_simulate_vv: 1 = CUDA-graph step with conditional rebuild node,
                                 * 0 = stream launches, -1 = graph construction failed (stream launches) */
+    int32_t n_prunes;          /* dual-list: refreshes of the inner (pruned) lists */
+    int32_t reserved2_;
     int32_t reserved_;         /* decomposed runs: the rebuild interval the next call will use (adapted from displacements) */
 } mb_stats_t;
 

@@ -24,6 +24,8 @@ struct Control {
     int disp;           // an atom moved more than skin/2 since the last build (fixed-interval policy)
     int overflow;       // bit0 halo capacity, bit1 list stride, bit2 special stride
     int violations;
+    int prune;          // gate: the inner (pruned) lists must be refreshed from the outer lists
+    int n_prunes;
     unsigned long long n_rebuilds;
     unsigned long long n_pairs;  // real full-shell entries of the last build
     int max_neighbors;
@@ -67,6 +69,8 @@ struct Geom {
     int align;    // atoms per 16 bytes of the lj2 array (2 for float, 1 for double)
     T rlist2;
     T skin_half2;
+    T rinner2;        // dual list: pairs within r_inner at prune time form the list the force kernel walks
+    T skin_in_half2;  // ((r_inner - max r_cut) / 2)^2
 };
 
 __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -591,11 +595,84 @@ __global__ void rebuild_finish_kernel(Control* ctl) {
         if (ctl->disp) ctl->violations++;
         ctl->disp = 0;
         ctl->rebuild = 0;
+        ctl->prune = 1;  // fresh outer lists: derive the inner lists from them
         ctl->n_rebuilds++;
         if (ctl->max_disp2_bits > ctl->call_max_disp2_bits) ctl->call_max_disp2_bits = ctl->max_disp2_bits;
         ctl->max_disp2_bits = 0;
     }
 }
+// ---- dual-list pruning -------------------------------------------------------------------------------
+// The lists built above hold every pair within r_list (outer radius). The force kernel walks a shorter inner
+// list: the pairs within r_inner = max r_cut + inner skin at the last prune, refreshed whenever an atom moved more
+// than half the inner skin (cheap: no cell search, the outer list is the candidate set). Same 16-bit halo indices,
+// same lane-swizzled layout, order preserved. One CTA per brick, 8 lanes per owned atom.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    prune_lists_kernel(const Control* __restrict__ ctl, Geom<T> g, const BrickHdr* __restrict__ hdrs, const Run* __restrict__ runs,
+                       const IRow* __restrict__ irows, const typename VT<T>::T4* __restrict__ pos4,
+                       const unsigned short* __restrict__ olist, const ushort2* __restrict__ ocounts,
+                       unsigned short* __restrict__ ilist, ushort2* __restrict__ icounts,
+                       typename VT<T>::T4* __restrict__ xprune4, int brick0) {
+    if (!ctl->prune) return;
+    using T4 = typename VT<T>::T4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = blockIdx.x + brick0;
+    const BrickHdr hd = hdrs[b];
+    if (hd.i_count == 0 || hd.halo_count > g.halo_cap) return;
+    T4* s_pos = reinterpret_cast<T4*>(smem_raw);
+    __shared__ uint64_t s_bar;
+    __shared__ IRow s_rows[64];
+    const int tid = threadIdx.x;
+    const Run* my_runs = runs + (size_t)b * g.max_runs;
+    for (int k = tid; k < g.n_irows; k += blockDim.x) s_rows[k] = irows[(size_t)b * g.n_irows + k];
+    stage_halo<T, false, false>(g, b, hd, my_runs, pos4, nullptr, s_pos, nullptr, &s_bar);
+    const int sub = tid >> 3, l = tid & 7;
+    const unsigned int sub_mask = 0xffu << (8 * (sub & 3));
+    const unsigned int lt = (1u << l) - 1u;
+    for (int task = sub; task < hd.i_count; task += 32) {
+        int q = 0;
+        while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
+        const IRow row = s_rows[q];
+        const int slot = row.slot_begin + (task - row.cum);
+        const int si = row.smem_begin + (task - row.cum);
+        const T4 pi = s_pos[si];
+        const ushort2 cnt = ocounts[slot];
+        const int n_groups = ((int)cnt.x + 31) >> 5;
+        const unsigned short* lp = olist + (size_t)slot * g.stride;
+        unsigned short* op = ilist + (size_t)slot * g.stride;
+        int out = 0;
+        for (int gi = 0; gi < n_groups; gi++) {
+            const uint2 w = reinterpret_cast<const uint2*>(lp + gi * 32)[l];
+            const int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {  // logical entry index inside the group = l + 8 e
+                const T4 pj = s_pos[j[e]];
+                const T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const bool in = (dx * dx + dy * dy + dz * dz) <= g.rinner2;
+                const unsigned int bal = (__ballot_sync(sub_mask, in) >> (8 * (sub & 3))) & 0xffu;
+                if (in) {
+                    const int m = out + __popc(bal & lt);
+                    op[(m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3)] = (unsigned short)j[e];
+                }
+                out += __popc(bal);
+            }
+        }
+        const int padded = (out + 31) & ~31;
+        for (int m = out + l; m < padded; m += 8) op[(m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3)] = 0;
+        if (l == 0) {
+            icounts[slot] = make_ushort2((unsigned short)out, cnt.y);
+            xprune4[slot] = pos4[slot];
+        }
+    }
+}
+__global__ void prune_finish_kernel(Control* ctl) {
+    if (!ctl->prune) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        ctl->prune = 0;
+        ctl->n_prunes++;
+    }
+}
+
 __global__ void rebuild_begin_kernel(Control* ctl) {
     if (!ctl->rebuild) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {

@@ -417,6 +417,7 @@ class Engine : public EngineBase {
         if (path_ == 1 && max_rc > r_list_)
             return set_error(MB_ERR_INVALID, "neighbour list radius is smaller than an interaction cutoff");
         skin_ = (path_ == 1) ? (any_nocut_nl ? 0.0 : r_list_ - max_rc) : 0.0;
+        max_rc_ = max_rc;
         P_.has_lj = 0;
         P_.coul_kind = COUL_NONE;
         P_.lj_rc2 = (T)0;
@@ -562,6 +563,16 @@ class Engine : public EngineBase {
         g.ncells = g.nc[0] * g.nc[1] * g.nc[2];
         g.rlist2 = (T)(r_list_ * r_list_);
         g.skin_half2 = (T)(0.25 * skin_ * skin_);
+        {
+            const char* nd = getenv("MOLLYB200_NO_DUAL");
+            const char* fr = getenv("MOLLYB200_INNER_SKIN_FRAC");
+            if (fr) inner_frac_ = std::min(1.0, std::max(0.05, atof(fr)));
+            dual_ = !(nd && nd[0] == '1') && !decomposed() && skin_ > 1e-6 && inner_frac_ < 0.999;
+            const double skin_in = dual_ ? skin_ * inner_frac_ : skin_;
+            const double r_in = dual_ ? max_rc_ + skin_in : r_list_;
+            g.rinner2 = (T)(r_in * r_in);
+            g.skin_in_half2 = dual_ ? (T)(0.25 * skin_in * skin_in) : std::numeric_limits<T>::infinity();
+        }
         const double rho_c = (double)n_ / g.ncells;
         const double bytes_per_atom = sizeof(T4) + (P_.uniform_lj ? 0 : sizeof(T2));
         const double smem_budget = (double)smem_optin_ - 4096;
@@ -776,6 +787,23 @@ class Engine : public EngineBase {
         return MB_OK;
     }
 
+    // gated refresh of the inner lists from the outer lists (dual-list pruning); no-op unless ctl->prune
+    int enqueue_prune() {
+        if (!dual_) return MB_OK;
+        const size_t smem = (size_t)g_.halo_cap * sizeof(T4);
+        MB_CUDA(cudaFuncSetAttribute(prune_lists_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_.begin(Prof::REBUILD);
+        prune_lists_kernel<T><<<g_.nbricks, 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
+                                                                d_irows_.as<IRow>(), d_pos4_.as<T4>(), d_list_.as<unsigned short>(),
+                                                                d_counts_.as<ushort2>(), d_ilist_.as<unsigned short>(),
+                                                                d_icounts_.as<ushort2>(), d_xprune4_.as<T4>(), 0);
+        prune_finish_kernel<<<1, 32, 0, stream_>>>(d_ctl_.as<Control>());
+        prof_.end(Prof::REBUILD);
+        launches_ += 2;
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
+
     // launch the list builder (count-only or real; with or without exclusion handling)
     int launch_build(bool count_only) {
         const size_t smem = build_smem_bytes();
@@ -888,9 +916,15 @@ class Engine : public EngineBase {
             g_.stride = std::max(stride, 32);
             g_.sstride = std::max(8, (std::max(c.max_special, max_special_host_) + 7) & ~7);
             MB_CUDA(d_list_.ensure((size_t)(n_ + 16) * g_.stride * sizeof(unsigned short)));
+            if (dual_) {
+                MB_CUDA(d_ilist_.ensure((size_t)(n_ + 16) * g_.stride * sizeof(unsigned short)));
+                MB_CUDA(d_icounts_.ensure((size_t)(n_ + 16) * sizeof(ushort2)));
+                MB_CUDA(d_xprune4_.ensure((size_t)(n_ + 16) * sizeof(T4)));
+            }
             MB_CUDA(d_slist_.ensure((size_t)(n_ + 16) * g_.sstride * sizeof(unsigned short)));
             // pass C: the real build. The positions are already sorted; the pipeline is idempotent.
             MB_TRY(enqueue_rebuild(true, false));
+            MB_TRY(enqueue_prune());
             MB_TRY(read_ctl(c));
             if (c.overflow) return set_error(MB_ERR_CAPACITY, "neighbour capacity overflow during first build");
             last_ctl_ = c;
@@ -911,8 +945,9 @@ class Engine : public EngineBase {
             prof_.begin(Prof::FORCE);
             kern<<<nbr, FORCE_THREADS, smem, stream_>>>(g_, P_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
                                                                d_irows_.as<IRow>(), d_pos4_.as<T4>(), d_lj2_.as<T2>(),
-                                                               d_list_.as<unsigned short>(), d_slist_.as<unsigned short>(),
-                                                               d_counts_.as<ushort2>(), out, brick0);
+                                                               (dual_ ? d_ilist_ : d_list_).template as<unsigned short>(),
+                                                               d_slist_.as<unsigned short>(),
+                                                               (dual_ ? d_icounts_ : d_counts_).template as<ushort2>(), out, brick0);
             prof_.end(Prof::FORCE);
             return MB_OK;
         };
@@ -1003,7 +1038,8 @@ class Engine : public EngineBase {
             return MB_OK;
         }
         ingest_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_, coords_dev, vels_dev, d_orig_.as<int>(), d_xref4_.as<T4>(),
-                                                  d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->rebuild);
+                                                  d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->rebuild,
+                                                  dual_ ? d_xprune4_.as<T4>() : nullptr, &d_ctl_.as<Control>()->prune);
         launches_++;
         if (decomposed()) {
             // every rank holds the full state here; rebuild unconditionally so that ownership is fresh
@@ -1013,6 +1049,7 @@ class Engine : public EngineBase {
             return MB_OK;
         }
         MB_TRY(enqueue_rebuild(true, false));
+        MB_TRY(enqueue_prune());
         return MB_OK;
     }
 
@@ -1117,7 +1154,8 @@ class Engine : public EngineBase {
         int* flag_ptr;
     };
     int enqueue_step(const StepCfg& c, int do_cm_now, bool clear_cm_after_k1, bool capture,
-                     cudaGraphConditionalHandle handle, cudaGraph_t graph, cudaGraph_t* body_out, bool host_rebuild_hint) {
+                     cudaGraphConditionalHandle handle, cudaGraph_t graph, cudaGraph_t* body_out, bool host_rebuild_hint,
+                     cudaGraphConditionalHandle handle_prune = 0, cudaGraph_t* body_prune_out = nullptr) {
         const bool dec = decomposed() && path_ == 1;
         const int s0 = dec ? own_s0_ : 0, n_own = dec ? own_n_ : (int)n_;
         const int nb = std::max(1, (n_own + 255) / 256);
@@ -1127,7 +1165,8 @@ class Engine : public EngineBase {
         prof_.begin(Prof::VV);
         vv_kick_drift_kernel<T><<<std::min(nb, 4 * sm_count_), 256, 0, stream_>>>(
             s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
-            c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0);
+            c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0, (dual_ && path_ == 1) ? d_xprune4_.as<T4>() : nullptr,
+            g_.skin_in_half2, handle_prune);
         prof_.end(Prof::VV);
         launches_++;
         if (clear_cm_after_k1) {
@@ -1153,6 +1192,17 @@ class Engine : public EngineBase {
             MB_CUDA(cudaGraphAddNode(&cnode, graph, deps, ndeps, &cp));
             *body_out = cp.conditional.phGraph_out[0];
             MB_CUDA(cudaStreamUpdateCaptureDependencies(stream_, &cnode, 1, cudaStreamSetCaptureDependencies));
+            if (dual_) {  // second IF node: refresh the inner lists (after a rebuild, or when the inner skin is used up)
+                cudaGraphNodeParams cq = {cudaGraphNodeTypeConditional};
+                cq.type = cudaGraphNodeTypeConditional;
+                cq.conditional.handle = handle_prune;
+                cq.conditional.type = cudaGraphCondTypeIf;
+                cq.conditional.size = 1;
+                cudaGraphNode_t pnode;
+                MB_CUDA(cudaGraphAddNode(&pnode, graph, &cnode, 1, &cq));
+                *body_prune_out = cq.conditional.phGraph_out[0];
+                MB_CUDA(cudaStreamUpdateCaptureDependencies(stream_, &pnode, 1, cudaStreamSetCaptureDependencies));
+            }
         } else if (dec) {
             if (host_rebuild_hint) {
                 // neighbour rebuild on a decomposed box: replicate positions and velocities, rebuild (identical sort on every
@@ -1165,6 +1215,7 @@ class Engine : public EngineBase {
             }
         } else {
             if (rebuild_every_ == 0 || host_rebuild_hint) MB_TRY(enqueue_rebuild(true, false));
+            MB_TRY(enqueue_prune());
         }
         const int s0b = dec ? own_s0_ : 0, n_ownb = dec ? own_n_ : (int)n_;  // ownership may have changed in the rebuild
         const int nb2 = std::max(1, (n_ownb + 255) / 256);
@@ -1193,12 +1244,12 @@ class Engine : public EngineBase {
     }
 
     struct GraphKey {
-        int path, do_cm, thermostat, geom_version, rebuild_every;
+        int path, do_cm, thermostat, geom_version, rebuild_every, dual;
         double dt, kT, prob;
         int64_t n;
         bool operator==(const GraphKey& o) const {
             return path == o.path && do_cm == o.do_cm && thermostat == o.thermostat && geom_version == o.geom_version &&
-                   rebuild_every == o.rebuild_every && dt == o.dt && kT == o.kT && prob == o.prob && n == o.n;
+                   rebuild_every == o.rebuild_every && dual == o.dual && dt == o.dt && kT == o.kT && prob == o.prob && n == o.n;
         }
     };
     void destroy_graph() {
@@ -1226,13 +1277,15 @@ class Engine : public EngineBase {
             return rc;
         };
         if (cudaGraphCreate(&graph_, 0) != cudaSuccess) return fail(MB_ERR_CUDA);
-        cudaGraphConditionalHandle handle = 0;
+        cudaGraphConditionalHandle handle = 0, handle_p = 0;
         if (path_ == 1 && cudaGraphConditionalHandleCreate(&handle, graph_, 0, cudaGraphCondAssignDefault) != cudaSuccess)
+            return fail(MB_ERR_CUDA);
+        if (path_ == 1 && dual_ && cudaGraphConditionalHandleCreate(&handle_p, graph_, 0, cudaGraphCondAssignDefault) != cudaSuccess)
             return fail(MB_ERR_CUDA);
         if (cudaStreamBeginCaptureToGraph(stream_, graph_, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess)
             return fail(MB_ERR_CUDA);
-        cudaGraph_t body = nullptr;
-        if (enqueue_step(c, c.do_cm, false, true, handle, graph_, &body, false) != MB_OK) return fail(MB_ERR_CUDA);
+        cudaGraph_t body = nullptr, body_p = nullptr;
+        if (enqueue_step(c, c.do_cm, false, true, handle, graph_, &body, false, handle_p, &body_p) != MB_OK) return fail(MB_ERR_CUDA);
         cudaGraph_t out = nullptr;
         if (cudaStreamEndCapture(stream_, &out) != cudaSuccess) return fail(MB_ERR_CUDA);
         const int64_t step_nodes = launches_ - launches_before;
@@ -1242,6 +1295,13 @@ class Engine : public EngineBase {
                 return fail(MB_ERR_CUDA);
             if (enqueue_rebuild(true, false) != MB_OK) return fail(MB_ERR_CUDA);
             if (cudaStreamEndCapture(stream_, &out) != cudaSuccess) return fail(MB_ERR_CUDA);
+            if (dual_) {
+                if (!body_p) return fail(MB_ERR_CUDA);
+                if (cudaStreamBeginCaptureToGraph(stream_, body_p, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+                    return fail(MB_ERR_CUDA);
+                if (enqueue_prune() != MB_OK) return fail(MB_ERR_CUDA);
+                if (cudaStreamEndCapture(stream_, &out) != cudaSuccess) return fail(MB_ERR_CUDA);
+            }
         }
         if (cudaGraphInstantiate(&graph_exec_, graph_, 0) != cudaSuccess) return fail(MB_ERR_CUDA);
         prof_.enabled = prof_was;
@@ -1333,7 +1393,7 @@ class Engine : public EngineBase {
         bool use_graph = graph_enabled_ && !graph_failed_ && !prof_.enabled && c.do_cm >= 0 && p->n_steps >= 4 &&
                          !(cm_pending && c.do_cm == 0) && !dec;  // the decomposed step issues NCCL calls with per-rebuild sizes
         if (use_graph) {
-            GraphKey key{path_, c.do_cm, c.thermostat ? 1 : 0, geom_version_, rebuild_every_, p->dt, p->andersen_kT, p->andersen_prob, n_};
+            GraphKey key{path_, c.do_cm, c.thermostat ? 1 : 0, geom_version_, rebuild_every_, dual_ ? 1 : 0, p->dt, p->andersen_kT, p->andersen_prob, n_};
             if (!graph_exec_ || !(key == graph_key_)) {
                 if (build_step_graph(c, key) != MB_OK) {
                     graph_failed_ = true;  // stay on the stream path for this context
@@ -1451,6 +1511,7 @@ class Engine : public EngineBase {
             o->max_neighbors = c.max_neighbors;
             o->max_halo = c.max_halo;
             o->violations = c.violations;
+            o->n_prunes = c.n_prunes;
         }
         if (path_ == 1 && have_list_) {
             o->n_list_entries = (int64_t)n_ * g_.stride;
@@ -1508,6 +1569,9 @@ class Engine : public EngineBase {
     DevBuf d_ex_ptr_, d_ex_idx_, d_sp_ptr_, d_sp_idx_;
     DevBuf d_cid_, d_perm_, d_cell_count_, d_cell_start_, d_cell_fill_;
     DevBuf d_hdrs_, d_runs_, d_irows_, d_hcs_, d_counts_, d_list_, d_slist_;
+    DevBuf d_ilist_, d_icounts_, d_xprune4_;  // dual list: inner (pruned) lists + positions at the last prune
+    bool dual_ = false;
+    double max_rc_ = 0, inner_frac_ = 0.4;
     DevBuf d_partial_, d_pe_partial_;
 };
 
