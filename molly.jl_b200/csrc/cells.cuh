@@ -360,11 +360,12 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
 // Stages pos4 (and optionally lj2) runs of brick b into shared memory with bulk async copies, then
 // converts the positions to the brick-local frame (origin = brick corner, periodic image applied) in
 // double so that i-j differences carry no box-size rounding error.
-template <typename T, bool WITH_LJ, bool ALWAYS_LOCALIZE>
-__device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickHdr& hd, const Run* __restrict__ my_runs,
-                                           const typename VT<T>::T4* __restrict__ pos4,
-                                           const typename VT<T>::T2* __restrict__ lj2,
-                                           typename VT<T>::T4* s_pos, typename VT<T>::T2* s_lj, uint64_t* bar) {
+// Phase 1: arm the mbarrier and issue the bulk copies (returns right after the issue; the copies are in flight).
+template <typename T, bool WITH_LJ>
+__device__ __forceinline__ void stage_halo_issue(const Geom<T>& g, const BrickHdr& hd, const Run* __restrict__ my_runs,
+                                                 const typename VT<T>::T4* __restrict__ pos4,
+                                                 const typename VT<T>::T2* __restrict__ lj2, typename VT<T>::T4* s_pos,
+                                                 typename VT<T>::T2* s_lj, uint64_t* bar) {
     using T4 = typename VT<T>::T4;
     using T2 = typename VT<T>::T2;
     const int tid = threadIdx.x;
@@ -391,6 +392,13 @@ __device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickH
             }
         }
     }
+}
+// Phase 2: wait for the copies, then re-centre bricks that hold periodic images.
+template <typename T, bool ALWAYS_LOCALIZE>
+__device__ __forceinline__ void stage_halo_wait(const Geom<T>& g, int b, const BrickHdr& hd, const Run* __restrict__ my_runs,
+                                                typename VT<T>::T4* s_pos, uint64_t* bar) {
+    using T4 = typename VT<T>::T4;
+    const int tid = threadIdx.x;
     mbar_wait(bar, 0);
     // Bricks whose halo holds no periodic image keep global coordinates: the pair loop only uses differences of
     // positions, which are exact in the same frame. Only bricks at the box boundary are re-centred.
@@ -420,6 +428,14 @@ __device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickH
         }
     }
     __syncthreads();
+}
+template <typename T, bool WITH_LJ, bool ALWAYS_LOCALIZE>
+__device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickHdr& hd, const Run* __restrict__ my_runs,
+                                           const typename VT<T>::T4* __restrict__ pos4,
+                                           const typename VT<T>::T2* __restrict__ lj2,
+                                           typename VT<T>::T4* s_pos, typename VT<T>::T2* s_lj, uint64_t* bar) {
+    stage_halo_issue<T, WITH_LJ>(g, hd, my_runs, pos4, lj2, s_pos, s_lj, bar);
+    stage_halo_wait<T, ALWAYS_LOCALIZE>(g, b, hd, my_runs, s_pos, bar);
 }
 
 // ---- R6: full-shell neighbour lists --------------------------------------------------------------

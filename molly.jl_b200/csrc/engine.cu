@@ -564,10 +564,12 @@ class Engine : public EngineBase {
         g.rlist2 = (T)(r_list_ * r_list_);
         g.skin_half2 = (T)(0.25 * skin_ * skin_);
         {
-            const char* nd = getenv("MOLLYB200_NO_DUAL");
+            // dual-list pruning is opt-in (MOLLYB200_DUAL=1): measured on B200 it shortens the force kernel by ~6 % but the
+            // prune passes cost more than that at the C2 / C3 skins (profiles/r01_dual_list.md)
+            const char* du = getenv("MOLLYB200_DUAL");
             const char* fr = getenv("MOLLYB200_INNER_SKIN_FRAC");
             if (fr) inner_frac_ = std::min(1.0, std::max(0.05, atof(fr)));
-            dual_ = !(nd && nd[0] == '1') && !decomposed() && skin_ > 1e-6 && inner_frac_ < 0.999;
+            dual_ = (du && du[0] == '1') && !decomposed() && skin_ > 1e-6 && inner_frac_ < 0.999;
             const double skin_in = dual_ ? skin_ * inner_frac_ : skin_;
             const double r_in = dual_ ? max_rc_ + skin_in : r_list_;
             g.rinner2 = (T)(r_in * r_in);

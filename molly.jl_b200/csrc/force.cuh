@@ -62,24 +62,40 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
     __shared__ IRow s_rows[64];
     const Run* my_runs = runs + (size_t)b * g.max_runs;
     for (int k = tid; k < g.n_irows; k += blockDim.x) s_rows[k] = irows[(size_t)b * g.n_irows + k];
-    stage_halo<T, !UNIFORM, false>(g, b, hd, my_runs, pos4, lj2, s_pos, s_lj, &s_bar);
+    stage_halo_issue<T, !UNIFORM>(g, hd, my_runs, pos4, lj2, s_pos, s_lj, &s_bar);  // TMA copies in flight from here
 
     constexpr int NSUB = FORCE_THREADS / LPA;
     const int sub = tid / LPA, l = tid % LPA;
     T e_acc = (T)0;
     T vir[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
-    // The trip count is CTA-uniform so that every lane reaches the shuffles below together; sub-warps
-    // past the end run with empty lists.
-    const int n_iter = (hd.i_count + NSUB - 1) / NSUB;
-    for (int it = 0; it < n_iter; it++) {
-        const int task = it * NSUB + sub;
+    // Task bookkeeping. A task = one owned atom handled by one group of LPA lanes. The loop below is software-
+    // pipelined: the list length and the first LIST_HALF index words of task t+1 are requested while task t is being
+    // evaluated, and those of the first task while the halo is still landing, so the global-memory latency of the
+    // neighbour-list stream is off the critical path (each CTA only runs ~4 tasks per lane group).
+    constexpr int LIST_HALF = (MB_LIST_BATCH >= 2) ? MB_LIST_BATCH / 2 : 1;
+    auto locate = [&](int task, int& slot, int& si) -> bool {
         const bool valid = task < hd.i_count;
         int q = 0;
         while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
         const IRow row = s_rows[q];
-        const int k_in_row = task - row.cum;
-        const int slot = valid ? row.slot_begin + k_in_row : 0;
-        const int si = valid ? row.smem_begin + k_in_row : 0;
+        slot = valid ? row.slot_begin + (task - row.cum) : 0;
+        si = valid ? row.smem_begin + (task - row.cum) : 0;
+        return valid;
+    };
+    const int words_in_row = g.stride >> 5;  // groups a row can hold
+    const int n_iter = (hd.i_count + NSUB - 1) / NSUB;
+    int slot, si;
+    bool valid = locate(sub, slot, si);  // s_rows is visible: stage_halo_issue synchronised the CTA
+    ushort2 cnt = valid ? counts[slot] : make_ushort2(0, 0);
+    uint2 wa[LIST_HALF];
+    if (LPA == 8) {
+        const uint2* lp2 = reinterpret_cast<const uint2*>(list + (size_t)slot * g.stride) + l;
+#pragma unroll
+        for (int u = 0; u < LIST_HALF; u++) wa[u] = (valid && u < words_in_row) ? ldg_stream_u2(lp2 + (size_t)u * 8) : make_uint2(0u, 0u);
+    }
+    stage_halo_wait<T, false>(g, b, hd, my_runs, s_pos, &s_bar);
+
+    for (int it = 0; it < n_iter; it++) {
         const T4 pi = s_pos[si];
         T lj_s_i = (T)0, lj_e_i = (T)0;
         if (!UNIFORM) {
@@ -88,13 +104,11 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
             lj_e_i = t.y;
         }
         const T kq_i = P.ke * pi.w;
-        const ushort2 cnt = valid ? counts[slot] : make_ushort2(0, 0);
         T fx = (T)0, fy = (T)0, fz = (T)0;
 #if MB_USE_F32X2
         float2 axx = make_float2(0.f, 0.f), ayy = axx, azz = axx;  // packed-f32 accumulators (two neighbours per lane)
         (void)axx; (void)ayy; (void)azz;
 #endif
-
         auto eval = [&](int j, auto special_tag) {
             constexpr bool SPECIAL = decltype(special_tag)::value;
             const T4 pj = s_pos[j];
@@ -182,19 +196,39 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
         // main list: groups of 32 entries; with LPA lanes each lane owns 32/LPA entries per group
         const int n_groups = ((int)cnt.x + 31) >> 5;
         const unsigned short* lp = list + (size_t)slot * g.stride;
+        // next task (if any): its list length is requested now, its first index words after the first half below
+        int nslot = 0, nsi = 0;
+        const bool nvalid = (it + 1 < n_iter) ? locate((it + 1) * NSUB + sub, nslot, nsi) : false;
+        ushort2 ncnt = nvalid ? counts[nslot] : make_ushort2(0, 0);
         if (LPA == 8) {
-            // all index words of up to LIST_BATCH groups are requested before the first one is consumed: one
-            // exposed global-memory latency per batch instead of one per group
-            constexpr int LIST_BATCH = MB_LIST_BATCH;
             const uint2* lp2 = reinterpret_cast<const uint2*>(lp) + l;
-            for (int g0 = 0; g0 < n_groups; g0 += LIST_BATCH) {
-                uint2 w[LIST_BATCH];
+            // second half of this task's first batch
+            uint2 wb[LIST_HALF];
 #pragma unroll
-                for (int u = 0; u < LIST_BATCH; u++)
-                    w[u] = (g0 + u < n_groups) ? ldg_stream_u2(lp2 + (size_t)(g0 + u) * 8) : make_uint2(0u, 0u);
+            for (int u = 0; u < LIST_HALF; u++)
+                wb[u] = (LIST_HALF + u < n_groups) ? ldg_stream_u2(lp2 + (size_t)(LIST_HALF + u) * 8) : make_uint2(0u, 0u);
 #pragma unroll
-                for (int u = 0; u < LIST_BATCH; u++)
-                    if (g0 + u < n_groups) eval4(w[u]);
+            for (int u = 0; u < LIST_HALF; u++)
+                if (u < n_groups) eval4(wa[u]);
+            // prefetch the next task's first half into the registers just consumed
+            {
+                const uint2* np2 = reinterpret_cast<const uint2*>(list + (size_t)nslot * g.stride) + l;
+#pragma unroll
+                for (int u = 0; u < LIST_HALF; u++)
+                    wa[u] = (nvalid && u < words_in_row) ? ldg_stream_u2(np2 + (size_t)u * 8) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < LIST_HALF; u++)
+                if (LIST_HALF + u < n_groups) eval4(wb[u]);
+            // rows longer than one batch
+            for (int g0 = 2 * LIST_HALF; g0 < n_groups; g0 += LIST_HALF) {
+                uint2 wc[LIST_HALF];
+#pragma unroll
+                for (int u = 0; u < LIST_HALF; u++)
+                    wc[u] = (g0 + u < n_groups) ? ldg_stream_u2(lp2 + (size_t)(g0 + u) * 8) : make_uint2(0u, 0u);
+#pragma unroll
+                for (int u = 0; u < LIST_HALF; u++)
+                    if (g0 + u < n_groups) eval4(wc[u]);
             }
         } else {
             // generic: logical entry m of a group lives at ((m & 7) << 2) + (m >> 3)
@@ -223,6 +257,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
             fz += shfl_xor(fz, o);
         }
         if (l == 0 && valid) out.f4[slot] = make4<T>(fx, fy, fz, (T)0);
+        slot = nslot; si = nsi; valid = nvalid; cnt = ncnt;
     }
     if (ENERGY) {
         // full shell: every pair was visited from both ends -> 1/2
