@@ -135,7 +135,21 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
         // four neighbours at once, stage by stage, so the four shared-memory loads and the four reciprocal
         // chains are independent and in flight together
         auto eval4 = [&](uint2 w) {
+#if defined(MB_ABL) && MB_ABL == 1  // ablation: no pair work at all (staging + list streaming + bookkeeping only)
+            fx += __uint_as_float((w.x ^ w.y) & 0x3f000000u);
+            return;
+#endif
             int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
+#if defined(MB_ABL) && MB_ABL == 2  // ablation: arithmetic without the shared-memory gathers
+            j[0] = j[1] = j[2] = j[3] = (int)(threadIdx.x & 7);
+#endif
+#if defined(MB_ABL) && MB_ABL == 3  // ablation: shared-memory gathers without the arithmetic
+            {
+                const T4 a0 = s_pos[j[0]], a1 = s_pos[j[1]], a2 = s_pos[j[2]], a3 = s_pos[j[3]];
+                fx += a0.x + a1.x + a2.x + a3.x;
+                return;
+            }
+#endif
             T4 pj[4];
             T2 lj[4];
 #pragma unroll
