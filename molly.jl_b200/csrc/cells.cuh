@@ -46,14 +46,13 @@ struct BrickHdr {
     int i_count;     // atoms owned by the brick
     unsigned int tx_pos, tx_lj;  // bytes the bulk copies deliver
     int any_shift;
-    int t_count;     // tasks = pairs of consecutive owned atoms ("duos") the force kernel hands to one lane group
-    int pad[2];
+    int pad[3];
 };
 struct Run {
     int gstart, count, soff, shift;  // shift packed: (wx+1) | (wy+1)<<2 | (wz+1)<<4
 };
 struct IRow {
-    int slot_begin, count, smem_begin, cum;  // cum = number of duo tasks in the rows before this one
+    int slot_begin, count, smem_begin, cum;
 };
 
 template <typename T>
@@ -321,8 +320,8 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
             int cs = cell_start[cid], ce = cell_start[cid + 1];
             int st = run.soff + (cs - run.gstart);
             int en = st + (ce - cs);
-            st = min(st, 16383);
-            en = min(en, 16383);
+            st = min(st, 65535);
+            en = min(en, 65535);
             se = make_ushort2((unsigned short)st, (unsigned short)en);
         }
         my_hcs[hc] = se;
@@ -330,7 +329,7 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
     __syncthreads();
     if (tid == 0) {
         IRow* my_rows = irows + (size_t)b * g.n_irows;
-        int cum = 0, atoms_owned = 0;
+        int cum = 0;
         for (int q = 0; q < g.n_irows; q++) {
             int iy = q % g.b[1], iz = q / g.b[1];
             IRow row = {0, 0, 0, cum};
@@ -342,17 +341,15 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
                 row.smem_begin = my_hcs[hc].x;
             }
             my_rows[q] = row;
-            cum += (row.count + 1) >> 1;
-            atoms_owned += row.count;
+            cum += row.count;
         }
         BrickHdr hd;
         hd.halo_count = s_total;
-        hd.i_count = atoms_owned;
-        hd.t_count = cum;
+        hd.i_count = cum;
         hd.tx_pos = s_tx_pos;
         hd.tx_lj = s_tx_lj;
         hd.any_shift = s_any;
-        hd.pad[0] = hd.pad[1] = 0;
+        hd.pad[0] = hd.pad[1] = hd.pad[2] = 0;
         hdrs[b] = hd;
         atomicMax(&ctl->max_halo, s_total);
         if (s_total > g.halo_cap) atomicOr(&ctl->overflow, 1);
@@ -441,16 +438,10 @@ __device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickH
     stage_halo_wait<T, ALWAYS_LOCALIZE>(g, b, hd, my_runs, s_pos, bar);
 }
 
-// ---- R6: full-shell neighbour lists, one per DUO ---------------------------------------------------------------
-// A duo = two consecutive owned atoms of a cell row (spatially adjacent). They share ONE list: the union of their
-// neighbourhoods. The force kernel loads every listed halo atom once and evaluates it against both atoms (packed
-// f32x2 arithmetic on sm_100), which halves the shared-memory gathers, the index traffic and the list bytes per
-// atom; the price is ~20 % more pair evaluations (entries in range of only one of the two).
-// Entry = 14-bit halo index | bit 14: skip for atom a | bit 15: skip for atom b (self, excluded or special pair).
-// One CTA per brick, one warp per duo. Special (1-4) pairs go to per-atom lists. The row of a
-// duo is stored at the slot of its first atom, in the lane-swizzled order the force kernel reads.
-constexpr unsigned short LIST_SKIP_A = 0x4000, LIST_SKIP_B = 0x8000, LIST_IDX_MASK = 0x3fff;
-
+// ---- R6: full-shell neighbour lists --------------------------------------------------------------
+// One CTA per brick, one warp per owned atom. Entries are 16-bit halo indices written in the lane-
+// swizzled order the force kernel reads (see force.cuh). Excluded pairs are dropped here; special
+// (1-4) pairs go to a separate short list.
 template <typename T, bool COUNT_ONLY, bool HAS_EX>
 __global__ void __launch_bounds__(256)
     build_lists_kernel(Control* __restrict__ ctl, Geom<T> g, const BrickHdr* __restrict__ hdrs,
@@ -488,155 +479,123 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
 
-    const T cyv = (T)g.celld[1], czv = (T)g.celld[2];
-    const T inv_cx = g.inv_cell[0];
-    const T rl2 = g.rlist2 * (T)1.0001;
     int my_max = 0;
     unsigned long long my_pairs = 0;
-    for (int task = wid; task < hd.t_count; task += nw) {
-        // locate the duo
+    for (int task = wid; task < hd.i_count; task += nw) {
+        // locate the owned atom
         int q = 0;
         while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
-        const IRow row = s_rows[q];
-        const int ka = 2 * (task - row.cum);
-        const bool has_b = ka + 1 < row.count;
-        const int slot_a = row.slot_begin + ka;
-        const int si_a = row.smem_begin + ka;
-        const int si_b = has_b ? si_a + 1 : 0;  // halo slot 0 is the far-away dummy
-        const int iy = q % g.b[1], iz = q / g.b[1];
-        // cells of the row that hold a and b
-        int ix_a = 0, ix_b;
+        IRow row = s_rows[q];
+        int k_in_row = task - row.cum;
+        int slot = row.slot_begin + k_in_row;
+        int si = row.smem_begin + k_in_row;
+        int iy = q % g.b[1], iz = q / g.b[1];
+        // which cell of the row holds it
+        int ix = 0;
         {
-            const int hc0 = ((iz + g.h) * g.H[1] + (iy + g.h)) * g.H[0] + g.h;
-            while (ix_a + 1 < g.b[0] && si_a >= (int)s_hcs[hc0 + ix_a].y) ix_a++;
-            ix_b = ix_a;
-            if (has_b)
-                while (ix_b + 1 < g.b[0] && si_b >= (int)s_hcs[hc0 + ix_b].y) ix_b++;
+            int hc0 = ((iz + g.h) * g.H[1] + (iy + g.h)) * g.H[0] + g.h;
+            while (ix + 1 < g.b[0] && si >= (int)s_hcs[hc0 + ix].y) ix++;
         }
-        const T4 pa = s_pos[si_a];
-        const T4 pb = s_pos[si_b];
-        const int oa = s_orig[si_a];
-        const int ob = has_b ? s_orig[si_b] : -1;
-        // exclusion / special partner lists of both atoms, spread over the lanes
-        int exa_a = 0, exa_n = 0, spa_a = 0, spa_n = 0, exb_a = 0, exb_n = 0, spb_a = 0, spb_n = 0;
-        int my_exa = -2, my_spa = -2, my_exb = -2, my_spb = -2;
-        if (HAS_EX) {
-            if (ex_ptr) { exa_a = ex_ptr[oa]; exa_n = ex_ptr[oa + 1] - exa_a; if (has_b) { exb_a = ex_ptr[ob]; exb_n = ex_ptr[ob + 1] - exb_a; } }
-            if (sp_ptr) { spa_a = sp_ptr[oa]; spa_n = sp_ptr[oa + 1] - spa_a; if (has_b) { spb_a = sp_ptr[ob]; spb_n = sp_ptr[ob + 1] - spb_a; } }
-            if (lane < exa_n) my_exa = ex_idx[exa_a + lane];
-            if (lane < exb_n) my_exb = ex_idx[exb_a + lane];
-            if (lane < spa_n) my_spa = sp_idx[spa_a + lane];
-            if (lane < spb_n) my_spb = sp_idx[spb_a + lane];
-        }
-        int count = 0, sc_a = 0, sc_b = 0, real_pairs = 0;
-        unsigned short* my_list = list + (size_t)slot_a * g.stride;
-        unsigned short* my_slist_a = slist + (size_t)slot_a * g.sstride;
-        unsigned short* my_slist_b = slist + (size_t)(slot_a + 1) * g.sstride;
-        // Only the part of each halo row that can hold a neighbour of a or b is scanned: with dy, dz the distance from
-        // the atom to the row's (y,z) cell slab, candidates need |dx| <= sqrt(r_list^2 - dy^2 - dz^2).
+        T4 pi = s_pos[si];
+        int oi = s_orig[si];
+        // exclusion / special partner lists of atom oi into lanes
+        int ex_a = ex_ptr ? ex_ptr[oi] : 0, ex_n = ex_ptr ? ex_ptr[oi + 1] - ex_a : 0;
+        int sp_a = sp_ptr ? sp_ptr[oi] : 0, sp_n = sp_ptr ? sp_ptr[oi + 1] - sp_a : 0;
+        int my_ex = (lane < ex_n) ? ex_idx[ex_a + lane] : -2;
+        int my_sp = (lane < sp_n) ? sp_idx[sp_a + lane] : -2;
+        int count = 0, scount = 0;
+        unsigned short* my_list = list + (size_t)slot * g.stride;
+        unsigned short* my_slist = slist + (size_t)slot * g.sstride;
+        // Only the part of each halo row that can hold a neighbour is scanned: with dy, dz the distance from the
+        // atom to the row's (y,z) cell slab, candidates need |dx| <= sqrt(r_list^2 - dy^2 - dz^2).
+        const T cyv = (T)g.celld[1], czv = (T)g.celld[2];
+        const T inv_cx = g.inv_cell[0];
+        const T rl2 = g.rlist2 * (T)1.0001;
         for (int rz = iz; rz <= iz + 2 * g.h; rz++) {
             const T zlo = (T)(rz - g.h) * czv;
-            const T dza = fmax(fmax(zlo - pa.z, pa.z - (zlo + czv)), (T)0);
-            const T dzb = fmax(fmax(zlo - pb.z, pb.z - (zlo + czv)), (T)0);
+            const T dzm = fmax(fmax(zlo - pi.z, pi.z - (zlo + czv)), (T)0);
             for (int ry = iy; ry <= iy + 2 * g.h; ry++) {
                 const T ylo = (T)(ry - g.h) * cyv;
-                const T dya = fmax(fmax(ylo - pa.y, pa.y - (ylo + cyv)), (T)0);
-                const T dyb = fmax(fmax(ylo - pb.y, pb.y - (ylo + cyv)), (T)0);
-                const T rem_a = rl2 - dya * dya - dza * dza;
-                const T rem_b = has_b ? rl2 - dyb * dyb - dzb * dzb : (T)-1;
-                if (rem_a < (T)0 && rem_b < (T)0) continue;
-                T xlo = (T)1e30, xhi = (T)-1e30;
-                if (rem_a >= (T)0) { const T w = fsqrt(rem_a) + (T)1e-4; xlo = pa.x - w; xhi = pa.x + w; }
-                if (rem_b >= (T)0) { const T w = fsqrt(rem_b) + (T)1e-4; xlo = fmin(xlo, pb.x - w); xhi = fmax(xhi, pb.x + w); }
-                int rx_lo = (int)ffloor(xlo * inv_cx) + g.h;
-                int rx_hi = (int)ffloor(xhi * inv_cx) + g.h;
-                rx_lo = max(rx_lo, ix_a);
-                rx_hi = min(rx_hi, ix_b + 2 * g.h);
-                const int hcrow = (rz * g.H[1] + ry) * g.H[0];
-                const int a = s_hcs[hcrow + rx_lo].x;
-                const int e = s_hcs[hcrow + rx_hi].y;
+                const T dym = fmax(fmax(ylo - pi.y, pi.y - (ylo + cyv)), (T)0);
+                const T rem = rl2 - dym * dym - dzm * dzm;
+                if (rem < (T)0) continue;
+                const T wx = fsqrt(rem) + (T)1e-4;
+                int rx_lo = (int)ffloor((pi.x - wx) * inv_cx) + g.h;
+                int rx_hi = (int)ffloor((pi.x + wx) * inv_cx) + g.h;
+                rx_lo = max(rx_lo, ix);
+                rx_hi = min(rx_hi, ix + 2 * g.h);
+                int hcrow = (rz * g.H[1] + ry) * g.H[0];
+                int a = s_hcs[hcrow + rx_lo].x;
+                int e = s_hcs[hcrow + rx_hi].y;
                 for (int cbase = a; cbase < e; cbase += 32) {
-                    const int c = cbase + lane;
-                    bool in_a = false, in_b = false;
-                    if (c < e) {
-                        const T4 pj = s_pos[c];
-                        const T ax = pa.x - pj.x, ay = pa.y - pj.y, az = pa.z - pj.z;
-                        const T bx = pb.x - pj.x, by = pb.y - pj.y, bz = pb.z - pj.z;
-                        in_a = (ax * ax + ay * ay + az * az) <= g.rlist2 && c != si_a;
-                        in_b = has_b && (bx * bx + by * by + bz * bz) <= g.rlist2 && c != si_b;
+                    int c = cbase + lane;
+                    bool in = false, special = false;
+                    if (c < e && c != si) {
+                        T4 pj = s_pos[c];
+                        T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                        T d2 = dx * dx + dy * dy + dz * dz;
+                        in = d2 <= g.rlist2;
                     }
-                    bool skip_a = (c == si_a), skip_b = (c == si_b) || !has_b;
-                    bool spec_a = false, spec_b = false;
-                    if (HAS_EX) {
-                        const int oj = (in_a || in_b) ? s_orig[c] : -1;
-                        // warp-uniform loops over the partner lists
-                        for (int k = 0; k < min(exa_n, 32); k++) if (__shfl_sync(0xffffffffu, my_exa, k) == oj) skip_a = true;
-                        for (int k = 32; k < exa_n; k++) if (ex_idx[exa_a + k] == oj) skip_a = true;
-                        for (int k = 0; k < min(exb_n, 32); k++) if (__shfl_sync(0xffffffffu, my_exb, k) == oj) skip_b = true;
-                        for (int k = 32; k < exb_n; k++) if (ex_idx[exb_a + k] == oj) skip_b = true;
-                        for (int k = 0; k < min(spa_n, 32); k++) if (__shfl_sync(0xffffffffu, my_spa, k) == oj) spec_a = true;
-                        for (int k = 32; k < spa_n; k++) if (sp_idx[spa_a + k] == oj) spec_a = true;
-                        for (int k = 0; k < min(spb_n, 32); k++) if (__shfl_sync(0xffffffffu, my_spb, k) == oj) spec_b = true;
-                        for (int k = 32; k < spb_n; k++) if (sp_idx[spb_a + k] == oj) spec_b = true;
-                        spec_a = spec_a && in_a && !skip_a;  // excluded wins over special
-                        spec_b = spec_b && in_b && !skip_b;
+                    int oj = (HAS_EX && in) ? s_orig[c] : -1;
+                    // exclusions (warp-uniform loops over the partner lists)
+                    if (HAS_EX && ex_n > 0) {
+                        int nn = min(ex_n, 32);
+                        for (int k = 0; k < nn; k++) {
+                            int v = __shfl_sync(0xffffffffu, my_ex, k);
+                            if (v == oj) in = false;
+                        }
+                        for (int k = 32; k < ex_n; k++)
+                            if (ex_idx[ex_a + k] == oj) in = false;
                     }
-                    const bool main_a = in_a && !skip_a && !spec_a;
-                    const bool main_b = in_b && !skip_b && !spec_b;
-                    const bool keep = main_a || main_b;
-                    const unsigned int kb_ = __ballot_sync(0xffffffffu, keep);
-                    const unsigned int sa_ = __ballot_sync(0xffffffffu, spec_a);
-                    const unsigned int sb_ = __ballot_sync(0xffffffffu, spec_b);
-                    const unsigned int ma_ = __ballot_sync(0xffffffffu, main_a);
-                    const unsigned int mb2_ = __ballot_sync(0xffffffffu, main_b);
-                    const unsigned int lt = (1u << lane) - 1u;
+                    if (HAS_EX && sp_n > 0) {
+                        int nn = min(sp_n, 32);
+                        for (int k = 0; k < nn; k++) {
+                            int v = __shfl_sync(0xffffffffu, my_sp, k);
+                            if (in && v == oj) special = true;
+                        }
+                        for (int k = 32; k < sp_n; k++)
+                            if (in && sp_idx[sp_a + k] == oj) special = true;
+                    }
+                    bool main_hit = in && !special;
+                    bool spec_hit = in && special;
+                    unsigned int mb_ = __ballot_sync(0xffffffffu, main_hit);
+                    unsigned int sb_ = __ballot_sync(0xffffffffu, spec_hit);
+                    unsigned int lt = (1u << lane) - 1u;
                     if (!COUNT_ONLY) {
-                        if (keep) {
-                            const int m = count + __popc(kb_ & lt);
+                        if (main_hit) {
+                            int m = count + __popc(mb_ & lt);
                             if (m < g.stride) {
-                                const int phys = (m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3);
-                                // an entry that is not a main pair of one atom is skipped for that atom (self / excluded /
-                                // special); being merely out of its range needs no flag, the cutoff test zeroes it
-                                unsigned short ent = (unsigned short)c;
-                                if (skip_a || spec_a) ent |= LIST_SKIP_A;
-                                if (skip_b || spec_b) ent |= LIST_SKIP_B;
-                                my_list[phys] = ent;
+                                int phys = (m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3);
+                                my_list[phys] = (unsigned short)c;
                             }
                         }
-                        if (spec_a) {
-                            const int m = sc_a + __popc(sa_ & lt);
-                            if (m < g.sstride) my_slist_a[m] = (unsigned short)c;
-                        }
-                        if (spec_b) {
-                            const int m = sc_b + __popc(sb_ & lt);
-                            if (m < g.sstride) my_slist_b[m] = (unsigned short)c;
+                        if (spec_hit) {
+                            int m = scount + __popc(sb_ & lt);
+                            if (m < g.sstride) my_slist[m] = (unsigned short)c;
                         }
                     }
-                    count += __popc(kb_);
-                    sc_a += __popc(sa_);
-                    sc_b += __popc(sb_);
-                    real_pairs += __popc(ma_) + __popc(mb2_) + __popc(sa_) + __popc(sb_);
+                    count += __popc(mb_);
+                    scount += __popc(sb_);
                 }
             }
         }
         if (!COUNT_ONLY) {
             // pad the last group of 32 with the dummy atom (halo slot 0)
-            const int padded = min((count + 31) & ~31, g.stride);
+            int padded = min((count + 31) & ~31, g.stride);
             for (int m = count + lane; m < padded; m += 32) {
-                const int phys = (m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3);
+                int phys = (m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3);
                 my_list[phys] = 0;
             }
             if (lane == 0) {
-                counts[slot_a] = make_ushort2((unsigned short)min(count, g.stride), (unsigned short)min(sc_a, g.sstride));
-                if (has_b) counts[slot_a + 1] = make_ushort2(0, (unsigned short)min(sc_b, g.sstride));
+                counts[slot] = make_ushort2((unsigned short)min(count, g.stride), (unsigned short)min(scount, g.sstride));
                 if (count > g.stride) atomicOr(&ctl->overflow, 2);
-                if (sc_a > g.sstride || sc_b > g.sstride) atomicOr(&ctl->overflow, 4);
+                if (scount > g.sstride) atomicOr(&ctl->overflow, 4);
             }
         }
         my_max = max(my_max, count);
         if (lane == 0) {
-            my_pairs += (unsigned long long)real_pairs;
-            atomicMax(&ctl->max_special, max(sc_a, sc_b));
+            my_pairs += (unsigned long long)(count + scount);
+            atomicMax(&ctl->max_special, scount);
         }
     }
     if (lane == 0) {
@@ -652,11 +611,84 @@ __global__ void rebuild_finish_kernel(Control* ctl) {
         if (ctl->disp) ctl->violations++;
         ctl->disp = 0;
         ctl->rebuild = 0;
+        ctl->prune = 1;  // fresh outer lists: derive the inner lists from them
         ctl->n_rebuilds++;
         if (ctl->max_disp2_bits > ctl->call_max_disp2_bits) ctl->call_max_disp2_bits = ctl->max_disp2_bits;
         ctl->max_disp2_bits = 0;
     }
 }
+// ---- dual-list pruning -------------------------------------------------------------------------------
+// The lists built above hold every pair within r_list (outer radius). The force kernel walks a shorter inner
+// list: the pairs within r_inner = max r_cut + inner skin at the last prune, refreshed whenever an atom moved more
+// than half the inner skin (cheap: no cell search, the outer list is the candidate set). Same 16-bit halo indices,
+// same lane-swizzled layout, order preserved. One CTA per brick, 8 lanes per owned atom.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    prune_lists_kernel(const Control* __restrict__ ctl, Geom<T> g, const BrickHdr* __restrict__ hdrs, const Run* __restrict__ runs,
+                       const IRow* __restrict__ irows, const typename VT<T>::T4* __restrict__ pos4,
+                       const unsigned short* __restrict__ olist, const ushort2* __restrict__ ocounts,
+                       unsigned short* __restrict__ ilist, ushort2* __restrict__ icounts,
+                       typename VT<T>::T4* __restrict__ xprune4, int brick0) {
+    if (!ctl->prune) return;
+    using T4 = typename VT<T>::T4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int b = blockIdx.x + brick0;
+    const BrickHdr hd = hdrs[b];
+    if (hd.i_count == 0 || hd.halo_count > g.halo_cap) return;
+    T4* s_pos = reinterpret_cast<T4*>(smem_raw);
+    __shared__ uint64_t s_bar;
+    __shared__ IRow s_rows[64];
+    const int tid = threadIdx.x;
+    const Run* my_runs = runs + (size_t)b * g.max_runs;
+    for (int k = tid; k < g.n_irows; k += blockDim.x) s_rows[k] = irows[(size_t)b * g.n_irows + k];
+    stage_halo<T, false, false>(g, b, hd, my_runs, pos4, nullptr, s_pos, nullptr, &s_bar);
+    const int sub = tid >> 3, l = tid & 7;
+    const unsigned int sub_mask = 0xffu << (8 * (sub & 3));
+    const unsigned int lt = (1u << l) - 1u;
+    for (int task = sub; task < hd.i_count; task += 32) {
+        int q = 0;
+        while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
+        const IRow row = s_rows[q];
+        const int slot = row.slot_begin + (task - row.cum);
+        const int si = row.smem_begin + (task - row.cum);
+        const T4 pi = s_pos[si];
+        const ushort2 cnt = ocounts[slot];
+        const int n_groups = ((int)cnt.x + 31) >> 5;
+        const unsigned short* lp = olist + (size_t)slot * g.stride;
+        unsigned short* op = ilist + (size_t)slot * g.stride;
+        int out = 0;
+        for (int gi = 0; gi < n_groups; gi++) {
+            const uint2 w = reinterpret_cast<const uint2*>(lp + gi * 32)[l];
+            const int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {  // logical entry index inside the group = l + 8 e
+                const T4 pj = s_pos[j[e]];
+                const T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const bool in = (dx * dx + dy * dy + dz * dz) <= g.rinner2;
+                const unsigned int bal = (__ballot_sync(sub_mask, in) >> (8 * (sub & 3))) & 0xffu;
+                if (in) {
+                    const int m = out + __popc(bal & lt);
+                    op[(m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3)] = (unsigned short)j[e];
+                }
+                out += __popc(bal);
+            }
+        }
+        const int padded = (out + 31) & ~31;
+        for (int m = out + l; m < padded; m += 8) op[(m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3)] = 0;
+        if (l == 0) {
+            icounts[slot] = make_ushort2((unsigned short)out, cnt.y);
+            xprune4[slot] = pos4[slot];
+        }
+    }
+}
+__global__ void prune_finish_kernel(Control* ctl) {
+    if (!ctl->prune) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        ctl->prune = 0;
+        ctl->n_prunes++;
+    }
+}
+
 __global__ void rebuild_begin_kernel(Control* ctl) {
     if (!ctl->rebuild) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {

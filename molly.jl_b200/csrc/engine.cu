@@ -569,8 +569,7 @@ class Engine : public EngineBase {
             const char* du = getenv("MOLLYB200_DUAL");
             const char* fr = getenv("MOLLYB200_INNER_SKIN_FRAC");
             if (fr) inner_frac_ = std::min(1.0, std::max(0.05, atof(fr)));
-            (void)du;
-            dual_ = false;  // dual-list pruning (tried in round 1, a net loss) is not wired to the duo lists
+            dual_ = (du && du[0] == '1') && !decomposed() && skin_ > 1e-6 && inner_frac_ < 0.999;
             const double skin_in = dual_ ? skin_ * inner_frac_ : skin_;
             const double r_in = dual_ ? max_rc_ + skin_in : r_list_;
             g.rinner2 = (T)(r_in * r_in);
@@ -595,7 +594,7 @@ class Engine : public EngineBase {
                         if (nranks_ > 1 && bz != 1) continue;  // slabs are whole cell layers
                         double halo = (bx + 4.0) * (by + 4.0) * (bz + 4.0) * rho_c * 1.25 + 64;
                         double smem = halo * bytes_per_atom;
-                        if (smem > smem_budget || halo > 15000) continue;
+                        if (smem > smem_budget || halo > 60000) continue;
                         double occ = std::min(8.0, std::floor(smem_budget / smem));
                         // latency hiding improves with resident CTAs (8 warps each): measured shape, saturating at ~6
                         static const double eff_tab[9] = {0.0, 0.35, 0.55, 0.70, 0.80, 0.88, 0.95, 0.97, 1.0};
@@ -819,7 +818,22 @@ class Engine : public EngineBase {
         return MB_OK;
     }
 
-    int enqueue_prune() { return MB_OK; }  // dual-list pruning was removed with the duo lists
+    // gated refresh of the inner lists from the outer lists (dual-list pruning); no-op unless ctl->prune
+    int enqueue_prune() {
+        if (!dual_) return MB_OK;
+        const size_t smem = (size_t)g_.halo_cap * sizeof(T4);
+        MB_CUDA(cudaFuncSetAttribute(prune_lists_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_.begin(Prof::REBUILD);
+        prune_lists_kernel<T><<<g_.nbricks, 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
+                                                                d_irows_.as<IRow>(), d_pos4_.as<T4>(), d_list_.as<unsigned short>(),
+                                                                d_counts_.as<ushort2>(), d_ilist_.as<unsigned short>(),
+                                                                d_icounts_.as<ushort2>(), d_xprune4_.as<T4>(), 0);
+        prune_finish_kernel<<<1, 32, 0, stream_>>>(d_ctl_.as<Control>());
+        prof_.end(Prof::REBUILD);
+        launches_ += 2;
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
 
     // launch the list builder (count-only or real; with or without exclusion handling)
     int launch_build(bool count_only) {
@@ -903,7 +917,7 @@ class Engine : public EngineBase {
             MB_TRY(choose_geometry());
             MB_TRY(alloc_brick_tables());
             // pass A: sort + tables with unlimited halo capacity to measure
-            g_.halo_cap = 16383;  // list entries carry 14-bit halo indices
+            g_.halo_cap = 65535;
             g_.stride = 0;
             g_.sstride = 0;
             MB_TRY(set_flag_rebuild());
@@ -912,9 +926,9 @@ class Engine : public EngineBase {
             MB_TRY(read_ctl(c));
             int cap = (int)(c.max_halo * (1.0 + 0.08 * cap_scale_)) + 32;  // temporal drift of the fullest brick's halo
             cap = (cap + 63) & ~63;
-            g_.halo_cap = std::min(cap, 16383);
+            g_.halo_cap = std::min(cap, 65535);
             size_t need = std::max(force_smem_bytes() + 2048, build_smem_bytes() + 1024);
-            if (c.max_halo >= 16300 || need > smem_optin_) {
+            if (c.max_halo >= 65000 || need > smem_optin_) {
                 // shrink the brick and retry
                 int* ub = user_b_;
                 int cur[3] = {g_.b[0], g_.b[1], g_.b[2]};

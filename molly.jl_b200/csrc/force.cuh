@@ -68,29 +68,25 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
     const int sub = tid / LPA, l = tid % LPA;
     T e_acc = (T)0;
     T vir[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
-    // A task = one DUO (two consecutive owned atoms a, b of a cell row, sharing one union neighbour list) handled by
-    // one group of LPA lanes: every listed halo atom is loaded from shared memory once and evaluated against both.
-    // The loop is software-pipelined: the list length and the first LIST_HALF index words of task t+1 are requested
-    // while task t is evaluated, and those of the first task while the halo is still landing.
+    // Task bookkeeping. A task = one owned atom handled by one group of LPA lanes. The loop below is software-
+    // pipelined: the list length and the first LIST_HALF index words of task t+1 are requested while task t is being
+    // evaluated, and those of the first task while the halo is still landing, so the global-memory latency of the
+    // neighbour-list stream is off the critical path (each CTA only runs ~4 tasks per lane group).
     constexpr int LIST_HALF = (MB_LIST_BATCH >= 2) ? MB_LIST_BATCH / 2 : 1;
-    auto locate = [&](int task, int& slot_a, int& si_a, bool& has_b) -> bool {
-        const bool valid = task < hd.t_count;
+    auto locate = [&](int task, int& slot, int& si) -> bool {
+        const bool valid = task < hd.i_count;
         int q = 0;
         while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
         const IRow row = s_rows[q];
-        const int ka = 2 * (task - row.cum);
-        slot_a = valid ? row.slot_begin + ka : 0;
-        si_a = valid ? row.smem_begin + ka : 0;
-        has_b = valid && (ka + 1 < row.count);
+        slot = valid ? row.slot_begin + (task - row.cum) : 0;
+        si = valid ? row.smem_begin + (task - row.cum) : 0;
         return valid;
     };
     const int words_in_row = g.stride >> 5;  // groups a row can hold
-    const int n_iter = (hd.t_count + NSUB - 1) / NSUB;
+    const int n_iter = (hd.i_count + NSUB - 1) / NSUB;
     int slot, si;
-    bool has_b;
-    bool valid = locate(sub, slot, si, has_b);  // s_rows is visible: stage_halo_issue synchronised the CTA
+    bool valid = locate(sub, slot, si);  // s_rows is visible: stage_halo_issue synchronised the CTA
     ushort2 cnt = valid ? counts[slot] : make_ushort2(0, 0);
-    ushort2 cntb = has_b ? counts[slot + 1] : make_ushort2(0, 0);  // .y = special count of atom b
     uint2 wa[LIST_HALF];
     if (LPA == 8) {
         const uint2* lp2 = reinterpret_cast<const uint2*>(list + (size_t)slot * g.stride) + l;
@@ -100,73 +96,84 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
     stage_halo_wait<T, false>(g, b, hd, my_runs, s_pos, &s_bar);
 
     for (int it = 0; it < n_iter; it++) {
-        const int sib = has_b ? si + 1 : 0;  // halo slot 0 = far-away dummy: a missing partner attracts nothing
-        const T4 pa = s_pos[si];
-        const T4 pb = s_pos[sib];
-        T lj_s_a = (T)0, lj_e_a = (T)0, lj_s_b = (T)0, lj_e_b = (T)0;
+        const T4 pi = s_pos[si];
+        T lj_s_i = (T)0, lj_e_i = (T)0;
         if (!UNIFORM) {
-            const T2 ta = s_lj[si], tb = s_lj[sib];
-            lj_s_a = ta.x; lj_e_a = ta.y;
-            lj_s_b = tb.x; lj_e_b = tb.y;
+            T2 t = s_lj[si];
+            lj_s_i = t.x;
+            lj_e_i = t.y;
         }
-        const T kq_a = P.ke * pa.w, kq_b = P.ke * pb.w;
-        T fax = (T)0, fay = (T)0, faz = (T)0, fbx = (T)0, fby = (T)0, fbz = (T)0;
+        const T kq_i = P.ke * pi.w;
+        T fx = (T)0, fy = (T)0, fz = (T)0;
 #if MB_USE_F32X2
-        float2 axx = make_float2(0.f, 0.f), ayy = axx, azz = axx;  // packed accumulators: (.x, .y) = (atom a, atom b)
+        float2 axx = make_float2(0.f, 0.f), ayy = axx, azz = axx;  // packed-f32 accumulators (two neighbours per lane)
         (void)axx; (void)ayy; (void)azz;
 #endif
-        // one neighbour against one atom (scalar path; also used for the special lists)
-        auto eval1 = [&](const T4& pi, T lj_s_i, T lj_e_i, T kq_i, const T4& pj, T lj_s_j, T lj_e_j, bool skip, auto special_tag,
-                         T& fx, T& fy, T& fz) {
+        auto eval = [&](int j, auto special_tag) {
             constexpr bool SPECIAL = decltype(special_tag)::value;
+            const T4 pj = s_pos[j];
+            T lj_s_j = (T)0, lj_e_j = (T)0;
+            if (!UNIFORM) {
+                T2 t = s_lj[j];
+                lj_s_j = t.x;
+                lj_e_j = t.y;
+            }
             const T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
             const T r2 = dx * dx + dy * dy + dz * dz;
             T fr, e;
             pair_eval<T, COUL, UNIFORM, SHIFT, ENERGY, SPECIAL>(P, r2, lj_s_i, lj_e_i, lj_s_j, lj_e_j, kq_i, pj.w, fr, e);
-            fr = skip ? (T)0 : fr;
             const T gx = fr * dx, gy = fr * dy, gz = fr * dz;
             fx += gx;
             fy += gy;
             fz += gz;
             if (ENERGY) {
-                e_acc += skip ? (T)0 : e;
+                e_acc += e;
                 vir[0] += dx * gx; vir[1] += dy * gy; vir[2] += dz * gz;
                 vir[3] += dx * gy; vir[4] += dx * gz; vir[5] += dy * gz;
             }
         };
-        // four list entries, each against both atoms of the duo
+        // four neighbours at once, stage by stage, so the four shared-memory loads and the four reciprocal
+        // chains are independent and in flight together
         auto eval4 = [&](uint2 w) {
 #if defined(MB_ABL) && MB_ABL == 1  // ablation: no pair work at all (staging + list streaming + bookkeeping only)
-            fax += __uint_as_float((w.x ^ w.y) & 0x3f000000u);
+            fx += __uint_as_float((w.x ^ w.y) & 0x3f000000u);
             return;
 #endif
-            const unsigned int raw[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+            int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
+#if defined(MB_ABL) && MB_ABL == 2  // ablation: arithmetic without the shared-memory gathers
+            j[0] = j[1] = j[2] = j[3] = (int)(threadIdx.x & 7);
+#endif
+#if defined(MB_ABL) && MB_ABL == 3  // ablation: shared-memory gathers without the arithmetic
+            {
+                const T4 a0 = s_pos[j[0]], a1 = s_pos[j[1]], a2 = s_pos[j[2]], a3 = s_pos[j[3]];
+                fx += a0.x + a1.x + a2.x + a3.x;
+                return;
+            }
+#endif
             T4 pj[4];
             T2 lj[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int j = (int)(raw[u] & LIST_IDX_MASK);
-                pj[u] = s_pos[j];
-                if (!UNIFORM) lj[u] = s_lj[j];
+                pj[u] = s_pos[j[u]];
+                if (!UNIFORM) lj[u] = s_lj[j[u]];
             }
 #if MB_USE_F32X2
             if constexpr (std::is_same<T, float>::value && UNIFORM && !SHIFT && !ENERGY && COUL == COUL_NONE) {
-                // Blackwell packed-f32 path (FFMA2 / FMUL2): the two atoms of the duo ride in one register pair, the
-                // neighbour's coordinates enter as broadcast scalars
-                const float2 pxx = make_float2(pa.x, pb.x), pyy = make_float2(pa.y, pb.y), pzz = make_float2(pa.z, pb.z);
-                const float2 one_m = make_float2(-1.f, -1.f);
+                // Blackwell packed-f32 path (FADD2 / FMUL2 / FFMA2): two neighbours per instruction
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const float2 dx = __ffma2_rn(make_float2(pj[u].x, pj[u].x), one_m, pxx);
-                    const float2 dy = __ffma2_rn(make_float2(pj[u].y, pj[u].y), one_m, pyy);
-                    const float2 dz = __ffma2_rn(make_float2(pj[u].z, pj[u].z), one_m, pzz);
+                for (int h2 = 0; h2 < 2; h2++) {
+                    const float4 a = pj[2 * h2], b = pj[2 * h2 + 1];
+                    const float2 one_m = make_float2(-1.f, -1.f);
+                    const float2 dx = __ffma2_rn(make_float2(a.x, b.x), one_m, make_float2(pi.x, pi.x));
+                    const float2 dy = __ffma2_rn(make_float2(a.y, b.y), one_m, make_float2(pi.y, pi.y));
+                    const float2 dz = __ffma2_rn(make_float2(a.z, b.z), one_m, make_float2(pi.z, pi.z));
                     const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
                     const float2 iv = make_float2(frcp(r2.x), frcp(r2.y));
                     const float2 i3 = __fmul2_rn(__fmul2_rn(iv, iv), iv);
                     const float2 tt = __ffma2_rn(make_float2(P.uni_A, P.uni_A), i3, make_float2(-P.uni_B, -P.uni_B));
                     float2 fr = __fmul2_rn(tt, __fmul2_rn(i3, iv));
-                    fr.x = (r2.x <= P.lj_rc2 && !(raw[u] & LIST_SKIP_A)) ? fr.x : 0.f;
-                    fr.y = (r2.y <= P.lj_rc2 && !(raw[u] & LIST_SKIP_B)) ? fr.y : 0.f;
+                    fr.x = (r2.x <= P.lj_rc2) ? fr.x : 0.f;
+                    fr.y = (r2.y <= P.lj_rc2) ? fr.y : 0.f;
                     axx = __ffma2_rn(fr, dx, axx);
                     ayy = __ffma2_rn(fr, dy, ayy);
                     azz = __ffma2_rn(fr, dz, azz);
@@ -174,25 +181,39 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
                 return;
             }
 #endif
+            T dx[4], dy[4], dz[4], r2[4], fr[4], e[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const T ljs = UNIFORM ? (T)0 : lj[u].x, lje = UNIFORM ? (T)0 : lj[u].y;
-                eval1(pa, lj_s_a, lj_e_a, kq_a, pj[u], ljs, lje, (raw[u] & LIST_SKIP_A) != 0, std::false_type{}, fax, fay, faz);
-                eval1(pb, lj_s_b, lj_e_b, kq_b, pj[u], ljs, lje, (raw[u] & LIST_SKIP_B) != 0, std::false_type{}, fbx, fby, fbz);
+                dx[u] = pi.x - pj[u].x;
+                dy[u] = pi.y - pj[u].y;
+                dz[u] = pi.z - pj[u].z;
+                r2[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                pair_eval<T, COUL, UNIFORM, SHIFT, ENERGY, false>(P, r2[u], lj_s_i, lj_e_i, UNIFORM ? (T)0 : lj[u].x,
+                                                                  UNIFORM ? (T)0 : lj[u].y, kq_i, pj[u].w, fr[u], e[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const T gx = fr[u] * dx[u], gy = fr[u] * dy[u], gz = fr[u] * dz[u];
+                fx += gx;
+                fy += gy;
+                fz += gz;
+                if (ENERGY) {
+                    e_acc += e[u];
+                    vir[0] += dx[u] * gx; vir[1] += dy[u] * gy; vir[2] += dz[u] * gz;
+                    vir[3] += dx[u] * gy; vir[4] += dx[u] * gz; vir[5] += dy[u] * gz;
+                }
             }
         };
 
         // main list: groups of 32 entries; with LPA lanes each lane owns 32/LPA entries per group
         const int n_groups = ((int)cnt.x + 31) >> 5;
         const unsigned short* lp = list + (size_t)slot * g.stride;
-        const int scnt_a = (int)cnt.y;
-        const int scnt_b = (int)cntb.y;
         // next task (if any): its list length is requested now, its first index words after the first half below
         int nslot = 0, nsi = 0;
-        bool nhas_b = false;
-        const bool nvalid = (it + 1 < n_iter) ? locate((it + 1) * NSUB + sub, nslot, nsi, nhas_b) : false;
+        const bool nvalid = (it + 1 < n_iter) ? locate((it + 1) * NSUB + sub, nslot, nsi) : false;
         ushort2 ncnt = nvalid ? counts[nslot] : make_ushort2(0, 0);
-        ushort2 ncntb = nhas_b ? counts[nslot + 1] : make_ushort2(0, 0);
         if (LPA == 8) {
             const uint2* lp2 = reinterpret_cast<const uint2*>(lp) + l;
             // second half of this task's first batch
@@ -224,53 +245,33 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
                     if (g0 + u < n_groups) eval4(wc[u]);
             }
         } else {
-            // generic lane count: logical entry m of a group lives at ((m & 7) << 2) + (m >> 3)
+            // generic: logical entry m of a group lives at ((m & 7) << 2) + (m >> 3)
             for (int gi = 0; gi < n_groups; gi++) {
                 for (int m = l; m < 32; m += LPA) {
-                    const int phys = ((m & 7) << 2) + (m >> 3);
-                    const unsigned int rawe = lp[gi * 32 + phys];
-                    const int j = (int)(rawe & LIST_IDX_MASK);
-                    const T4 pj = s_pos[j];
-                    T2 ljj = make2<T>((T)0, (T)0);
-                    if (!UNIFORM) ljj = s_lj[j];
-                    eval1(pa, lj_s_a, lj_e_a, kq_a, pj, ljj.x, ljj.y, (rawe & LIST_SKIP_A) != 0, std::false_type{}, fax, fay, faz);
-                    eval1(pb, lj_s_b, lj_e_b, kq_b, pj, ljj.x, ljj.y, (rawe & LIST_SKIP_B) != 0, std::false_type{}, fbx, fby, fbz);
+                    int phys = ((m & 7) << 2) + (m >> 3);
+                    eval((int)lp[gi * 32 + phys], std::false_type{});
                 }
             }
         }
-        // special (1-4) pairs, per atom
-        for (int m = l; m < scnt_a; m += LPA) {
-            const int j = (int)slist[(size_t)slot * g.sstride + m];
-            const T4 pj = s_pos[j];
-            T2 ljj = make2<T>((T)0, (T)0);
-            if (!UNIFORM) ljj = s_lj[j];
-            eval1(pa, lj_s_a, lj_e_a, kq_a, pj, ljj.x, ljj.y, false, std::true_type{}, fax, fay, faz);
-        }
-        for (int m = l; m < scnt_b; m += LPA) {
-            const int j = (int)slist[(size_t)(slot + 1) * g.sstride + m];
-            const T4 pj = s_pos[j];
-            T2 ljj = make2<T>((T)0, (T)0);
-            if (!UNIFORM) ljj = s_lj[j];
-            eval1(pb, lj_s_b, lj_e_b, kq_b, pj, ljj.x, ljj.y, false, std::true_type{}, fbx, fby, fbz);
-        }
+        // special (1-4) pairs
+        for (int m = l; m < (int)cnt.y; m += LPA) eval((int)slist[(size_t)slot * g.sstride + m], std::true_type{});
 #if MB_USE_F32X2
         if constexpr (std::is_same<T, float>::value) {
-            fax += axx.x; fay += ayy.x; faz += azz.x;
-            fbx += axx.y; fby += ayy.y; fbz += azz.y;
+            fx += axx.x + axx.y;
+            fy += ayy.x + ayy.y;
+            fz += azz.x + azz.y;
         }
 #endif
         // reduce the LPA partial forces
         __syncwarp();
 #pragma unroll
         for (int o = LPA >> 1; o > 0; o >>= 1) {
-            fax += shfl_xor(fax, o); fay += shfl_xor(fay, o); faz += shfl_xor(faz, o);
-            fbx += shfl_xor(fbx, o); fby += shfl_xor(fby, o); fbz += shfl_xor(fbz, o);
+            fx += shfl_xor(fx, o);
+            fy += shfl_xor(fy, o);
+            fz += shfl_xor(fz, o);
         }
-        if (l == 0 && valid) {
-            out.f4[slot] = make4<T>(fax, fay, faz, (T)0);
-            if (has_b) out.f4[slot + 1] = make4<T>(fbx, fby, fbz, (T)0);
-        }
-        slot = nslot; si = nsi; valid = nvalid; cnt = ncnt; cntb = ncntb; has_b = nhas_b;
+        if (l == 0 && valid) out.f4[slot] = make4<T>(fx, fy, fz, (T)0);
+        slot = nslot; si = nsi; valid = nvalid; cnt = ncnt;
     }
     if (ENERGY) {
         // full shell: every pair was visited from both ends -> 1/2
