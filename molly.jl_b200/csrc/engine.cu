@@ -565,7 +565,7 @@ class Engine : public EngineBase {
         g.skin_half2 = (T)(0.25 * skin_ * skin_);
         {
             // dual-list pruning is opt-in (MOLLYB200_DUAL=1): measured on B200 it shortens the force kernel by ~6 % but the
-            // prune passes cost more than that at the C2 / C3 skins (profiles/r01_dual_list.md)
+            // prune passes cost more than that at the C2 / C3 skins (profiles/r01_experiments.md)
             const char* du = getenv("MOLLYB200_DUAL");
             const char* fr = getenv("MOLLYB200_INNER_SKIN_FRAC");
             if (fr) inner_frac_ = std::min(1.0, std::max(0.05, atof(fr)));
