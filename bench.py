@@ -357,8 +357,12 @@ def main():
             "config": {"workload": label, "n_atoms": n, "dt_ps": dt, "r_cut_nm": rc, "r_list_nm": r_list,
                        "rebuild_policy": "displacement-triggered" if args.rebuild_every == 0 else f"every {args.rebuild_every}",
                        "parallelism": "single GPU" if world == 1 else (
-                           f"spatial decomposition: {world} z-slabs, NCCL halo exchange of positions per step, all-gather at "
-                           f"rebuilds (every 20 steps)" if decomposed else f"{world} independent replicas (one per GPU)"),
+                           f"spatial decomposition: {world} z-slabs; per step: "
+                           + ("halo positions stored into the neighbours' arrays over NVLink peer memory by the drift kernel, "
+                              "24-byte all-to-all of sum(m v) by the kick kernel" if st1.get("peer_transport")
+                              else "NCCL send/recv halo exchange + 24-byte all-reduce")
+                           + f"; NCCL all-gather at rebuilds (every {st1.get('reserved_', 0)} steps, adapted from displacements)"
+                           if decomposed else f"{world} independent replicas (one per GPU)"),
                        "brick_dims": st1["brick_dims"], "list_stride": st1["list_stride"], "n_bricks": st1["n_bricks"],
                        "l2": "not flushed between steps: step k+1 consumes the state step k wrote; per-step working set = "
                              f"{(st1['n_list_entries'] * 2 + n * 80) / 1e6:.0f} MB (neighbour list + state) vs 126 MB L2"},

@@ -83,7 +83,8 @@ typedef struct {
     int32_t graph_mode;        /* last mb_simulate_vv: 1 = CUDA-graph step with conditional rebuild node,
                                 * 0 = stream launches, -1 = graph construction failed (stream launches) */
     int32_t n_prunes;          /* dual-list: refreshes of the inner (pruned) lists */
-    int32_t reserved2_;
+    int32_t peer_transport;    /* decomposed runs: 1 = halo exchange and sum(m v) over NVLink peer memory (IPC-mapped
+                                * stores fused into the drift / kick kernels), 0 = NCCL send/recv + all-reduce */
     int32_t reserved_;         /* decomposed runs: the rebuild interval the next call will use (adapted from displacements) */
 } mb_stats_t;
 

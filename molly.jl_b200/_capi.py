@@ -39,7 +39,7 @@ class MBStats(C.Structure):
         ("violations", C.c_int32), ("r_list", C.c_double), ("kernel_launches", C.c_int64),
         ("force_ms", C.c_double), ("vv_ms", C.c_double), ("rebuild_ms", C.c_double),
         ("force_launches", C.c_int64), ("vv_launches", C.c_int64), ("rebuild_launches", C.c_int64),
-        ("graph_mode", C.c_int32), ("n_prunes", C.c_int32), ("reserved2_", C.c_int32), ("reserved_", C.c_int32),
+        ("graph_mode", C.c_int32), ("n_prunes", C.c_int32), ("peer_transport", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -507,76 +507,99 @@ __global__ void __launch_bounds__(256)
         unsigned short* my_list = list + (size_t)slot * g.stride;
         unsigned short* my_slist = slist + (size_t)slot * g.sstride;
         // Only the part of each halo row that can hold a neighbour is scanned: with dy, dz the distance from the
-        // atom to the row's (y,z) cell slab, candidates need |dx| <= sqrt(r_list^2 - dy^2 - dz^2).
+        // atom to the row's (y,z) cell slab, candidates need |dx| <= sqrt(r_list^2 - dy^2 - dz^2). The (2h+1)^2 rows
+        // are handled 32 at a time: lane r trims row r, a warp scan turns the row lengths into offsets, and the
+        // candidates of all rows are then walked as ONE flattened range (every lane busy; a 5-step shuffle search
+        // maps a flattened index back to its row). Entry order = row-major, as a row-by-row scan would give.
         const T cyv = (T)g.celld[1], czv = (T)g.celld[2];
         const T inv_cx = g.inv_cell[0];
         const T rl2 = g.rlist2 * (T)1.0001;
-        for (int rz = iz; rz <= iz + 2 * g.h; rz++) {
-            const T zlo = (T)(rz - g.h) * czv;
-            const T dzm = fmax(fmax(zlo - pi.z, pi.z - (zlo + czv)), (T)0);
-            for (int ry = iy; ry <= iy + 2 * g.h; ry++) {
+        const int side = 2 * g.h + 1, nrows = side * side;
+        for (int rb = 0; rb < nrows; rb += 32) {
+            const int r = rb + lane;
+            int ra = 0, rlen = 0;
+            if (r < nrows) {
+                const int rz = iz + r / side, ry = iy + r % side;
+                const T zlo = (T)(rz - g.h) * czv;
+                const T dzm = fmax(fmax(zlo - pi.z, pi.z - (zlo + czv)), (T)0);
                 const T ylo = (T)(ry - g.h) * cyv;
                 const T dym = fmax(fmax(ylo - pi.y, pi.y - (ylo + cyv)), (T)0);
                 const T rem = rl2 - dym * dym - dzm * dzm;
-                if (rem < (T)0) continue;
-                const T wx = fsqrt(rem) + (T)1e-4;
-                int rx_lo = (int)ffloor((pi.x - wx) * inv_cx) + g.h;
-                int rx_hi = (int)ffloor((pi.x + wx) * inv_cx) + g.h;
-                rx_lo = max(rx_lo, ix);
-                rx_hi = min(rx_hi, ix + 2 * g.h);
-                int hcrow = (rz * g.H[1] + ry) * g.H[0];
-                int a = s_hcs[hcrow + rx_lo].x;
-                int e = s_hcs[hcrow + rx_hi].y;
-                for (int cbase = a; cbase < e; cbase += 32) {
-                    int c = cbase + lane;
-                    bool in = false, special = false;
-                    if (c < e && c != si) {
-                        T4 pj = s_pos[c];
-                        T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                        T d2 = dx * dx + dy * dy + dz * dz;
-                        in = d2 <= g.rlist2;
-                    }
-                    int oj = (HAS_EX && in) ? s_orig[c] : -1;
-                    // exclusions (warp-uniform loops over the partner lists)
-                    if (HAS_EX && ex_n > 0) {
-                        int nn = min(ex_n, 32);
-                        for (int k = 0; k < nn; k++) {
-                            int v = __shfl_sync(0xffffffffu, my_ex, k);
-                            if (v == oj) in = false;
-                        }
-                        for (int k = 32; k < ex_n; k++)
-                            if (ex_idx[ex_a + k] == oj) in = false;
-                    }
-                    if (HAS_EX && sp_n > 0) {
-                        int nn = min(sp_n, 32);
-                        for (int k = 0; k < nn; k++) {
-                            int v = __shfl_sync(0xffffffffu, my_sp, k);
-                            if (in && v == oj) special = true;
-                        }
-                        for (int k = 32; k < sp_n; k++)
-                            if (in && sp_idx[sp_a + k] == oj) special = true;
-                    }
-                    bool main_hit = in && !special;
-                    bool spec_hit = in && special;
-                    unsigned int mb_ = __ballot_sync(0xffffffffu, main_hit);
-                    unsigned int sb_ = __ballot_sync(0xffffffffu, spec_hit);
-                    unsigned int lt = (1u << lane) - 1u;
-                    if (!COUNT_ONLY) {
-                        if (main_hit) {
-                            int m = count + __popc(mb_ & lt);
-                            if (m < g.stride) {
-                                int phys = (m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3);
-                                my_list[phys] = (unsigned short)c;
-                            }
-                        }
-                        if (spec_hit) {
-                            int m = scount + __popc(sb_ & lt);
-                            if (m < g.sstride) my_slist[m] = (unsigned short)c;
-                        }
-                    }
-                    count += __popc(mb_);
-                    scount += __popc(sb_);
+                if (rem >= (T)0) {
+                    const T wx = fsqrt(rem) + (T)1e-4;
+                    int rx_lo = (int)ffloor((pi.x - wx) * inv_cx) + g.h;
+                    int rx_hi = (int)ffloor((pi.x + wx) * inv_cx) + g.h;
+                    rx_lo = max(rx_lo, ix);
+                    rx_hi = min(rx_hi, ix + 2 * g.h);
+                    const int hcrow = (rz * g.H[1] + ry) * g.H[0];
+                    ra = s_hcs[hcrow + rx_lo].x;
+                    rlen = max((int)s_hcs[hcrow + rx_hi].y - ra, 0);
                 }
+            }
+            int inc = rlen;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const int roff = inc - rlen;  // exclusive offset of this lane's row in the flattened range
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            for (int k0 = 0; k0 < total; k0 += 32) {
+                const int k = k0 + lane;
+                int lo = 0;  // last row whose offset is <= k (empty rows share their successor's offset)
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) {
+                    int v = __shfl_sync(0xffffffffu, roff, lo + st);
+                    if (v <= k) lo += st;
+                }
+                const int c = __shfl_sync(0xffffffffu, ra, lo) + (k - __shfl_sync(0xffffffffu, roff, lo));
+                bool in = false, special = false;
+                if (k < total && c != si) {
+                    T4 pj = s_pos[c];
+                    T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                    T d2 = dx * dx + dy * dy + dz * dz;
+                    in = d2 <= g.rlist2;
+                }
+                int oj = (HAS_EX && in) ? s_orig[c] : -1;
+                // exclusions (warp-uniform loops over the partner lists)
+                if (HAS_EX && ex_n > 0) {
+                    int nn = min(ex_n, 32);
+                    for (int kk = 0; kk < nn; kk++) {
+                        int v = __shfl_sync(0xffffffffu, my_ex, kk);
+                        if (v == oj) in = false;
+                    }
+                    for (int kk = 32; kk < ex_n; kk++)
+                        if (ex_idx[ex_a + kk] == oj) in = false;
+                }
+                if (HAS_EX && sp_n > 0) {
+                    int nn = min(sp_n, 32);
+                    for (int kk = 0; kk < nn; kk++) {
+                        int v = __shfl_sync(0xffffffffu, my_sp, kk);
+                        if (in && v == oj) special = true;
+                    }
+                    for (int kk = 32; kk < sp_n; kk++)
+                        if (in && sp_idx[sp_a + kk] == oj) special = true;
+                }
+                bool main_hit = in && !special;
+                bool spec_hit = in && special;
+                unsigned int mb_ = __ballot_sync(0xffffffffu, main_hit);
+                unsigned int sb_ = __ballot_sync(0xffffffffu, spec_hit);
+                unsigned int lt = (1u << lane) - 1u;
+                if (!COUNT_ONLY) {
+                    if (main_hit) {
+                        int m = count + __popc(mb_ & lt);
+                        if (m < g.stride) {
+                            int phys = (m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3);
+                            my_list[phys] = (unsigned short)c;
+                        }
+                    }
+                    if (spec_hit) {
+                        int m = scount + __popc(sb_ & lt);
+                        if (m < g.sstride) my_slist[m] = (unsigned short)c;
+                    }
+                }
+                count += __popc(mb_);
+                scount += __popc(sb_);
             }
         }
         if (!COUNT_ONLY) {

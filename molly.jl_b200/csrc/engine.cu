@@ -140,6 +140,7 @@ struct Nccl {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
         if (lib) return true;
@@ -156,6 +157,7 @@ struct Nccl {
         MB_SYM(Recv, "ncclRecv");
         MB_SYM(Broadcast, "ncclBroadcast");
         MB_SYM(AllReduce, "ncclAllReduce");
+        MB_SYM(AllGather, "ncclAllGather");
         MB_SYM(GetErrorString, "ncclGetErrorString");
 #undef MB_SYM
         return true;
@@ -259,6 +261,7 @@ class Engine : public EngineBase {
     }
     ~Engine() override {
         destroy_graph();
+        p2p_close();
         if (own_stream_) cudaStreamDestroy(stream_);
     }
 
@@ -725,8 +728,26 @@ class Engine : public EngineBase {
         own_s0_ = layer_start_[layer_lo(rank_)];
         own_n_ = layer_start_[layer_lo(rank_ + 1)] - own_s0_;
         decomp_plan(ncz, g_.h, nranks_, rank_, layer_start_.data(), halo_send_, halo_recv_);
+        // The peer-memory transport carries at most MB_MAX_SEG segments / peers per rank. Whether the plan fits must be
+        // the same answer on every rank and every step, so it is evaluated for all ranks on unit-sized layers
+        // (the segment structure depends only on ncz, h and the rank count).
+        if (plan_key_[0] != ncz || plan_key_[1] != g_.h || plan_key_[2] != nranks_) {
+            plan_key_[0] = ncz; plan_key_[1] = g_.h; plan_key_[2] = nranks_;
+            std::vector<int> unit(ncz + 1);
+            for (int l = 0; l <= ncz; l++) unit[l] = l;
+            plan_fits_ = nranks_ <= MB_MAX_RANKS;
+            std::vector<DecompSeg> sd, rv;
+            std::vector<int> a, b;
+            for (int q = 0; q < nranks_ && plan_fits_; q++) {
+                decomp_plan(ncz, g_.h, nranks_, q, unit.data(), sd, rv);
+                distinct_peers(sd, a);
+                distinct_peers(rv, b);
+                if ((int)sd.size() > MB_MAX_SEG || (int)a.size() > MB_MAX_SEG || (int)b.size() > MB_MAX_SEG) plan_fits_ = false;
+            }
+        }
         return MB_OK;
     }
+    bool p2p_active() const { return p2p_ && plan_fits_; }
     // Decomposed runs rebuild at a fixed interval (every rank must take the same branch without a host round trip).
     // The interval for the NEXT call is derived from the largest displacement any interval of this call reached:
     // n_next = 0.8 * n * (skin/2) / d_max, agreed between ranks with one max-all-reduce. Violations are still counted.
@@ -772,9 +793,139 @@ class Engine : public EngineBase {
         MB_NCCL(g_nccl.GroupEnd());
         return MB_OK;
     }
+    // ---- peer-memory transport (peer.cuh) -------------------------------------------------------------------
+    void p2p_close() {
+        for (int r = 0; r < (int)peer_pos_.size(); r++) {
+            if (r == rank_) continue;
+            if (peer_pos_[r]) cudaIpcCloseMemHandle(peer_pos_[r]);
+            if (peer_comm_[r]) cudaIpcCloseMemHandle(peer_comm_[r]);
+        }
+        peer_pos_.clear();
+        peer_comm_.clear();
+        p2p_ = false;
+        p2p_pos_base_ = nullptr;
+    }
+    // Collective: every rank exports its position array and its PeerComm block as CUDA IPC handles, the handles travel
+    // by one ncclAllGather, and every rank maps the others'. Any failure on any rank (no peer access, IPC not permitted
+    // in this container, too many ranks) leaves ALL ranks on the NCCL transport.
+    int p2p_setup() {
+        if (p2p_pos_base_ == d_pos4_.p && !peer_pos_.empty()) return MB_OK;  // mapping is current
+        p2p_close();
+        p2p_pos_base_ = d_pos4_.p;
+        peer_pos_.assign(nranks_, nullptr);
+        peer_comm_.assign(nranks_, nullptr);
+        const char* env = getenv("MOLLYB200_P2P");
+        int ok = !(env && env[0] == '0') && nranks_ <= MB_MAX_RANKS;
+        struct Rec { cudaIpcMemHandle_t pos, comm; };
+        static_assert(sizeof(Rec) == 128, "two 64-byte IPC handles");
+        // 2 MiB so the block is an allocation of its own; zeroed before any peer can learn its address
+        MB_CUDA(d_comm_.ensure(2u << 20));
+        MB_CUDA(cudaMemsetAsync(d_comm_.p, 0, sizeof(PeerComm), stream_));
+        const unsigned long long magic = 0x6d62323030ull + (unsigned long long)rank_;
+        MB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(d_comm_.p) + offsetof(PeerComm, magic), &magic, sizeof(magic),
+                                cudaMemcpyHostToDevice, stream_));
+        Rec mine;
+        memset(&mine, 0, sizeof(mine));
+        if (ok && cudaIpcGetMemHandle(&mine.pos, d_pos4_.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        if (ok && cudaIpcGetMemHandle(&mine.comm, d_comm_.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        MB_CUDA(d_ipc_.ensure((size_t)(nranks_ + 1) * sizeof(Rec) + 16));
+        Rec* d_all = d_ipc_.as<Rec>();
+        MB_CUDA(cudaMemcpyAsync(d_all + nranks_, &mine, sizeof(Rec), cudaMemcpyHostToDevice, stream_));
+        MB_NCCL(g_nccl.AllGather(d_all + nranks_, d_all, sizeof(Rec), ncclChar, comm_, stream_));
+        std::vector<Rec> all(nranks_);
+        MB_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)nranks_ * sizeof(Rec), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        for (int r = 0; r < nranks_ && ok; r++) {
+            if (r == rank_) { peer_pos_[r] = d_pos4_.p; peer_comm_[r] = d_comm_.p; continue; }
+            if (cudaIpcOpenMemHandle(&peer_pos_[r], all[r].pos, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&peer_comm_[r], all[r].comm, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = 0;
+                cudaGetLastError();
+                break;
+            }
+            unsigned long long got = 0;  // the mapping must show the owner's tag
+            if (cudaMemcpy(&got, reinterpret_cast<char*>(peer_comm_[r]) + offsetof(PeerComm, magic), sizeof(got),
+                           cudaMemcpyDeviceToHost) != cudaSuccess || got != 0x6d62323030ull + (unsigned long long)r) {
+                ok = 0;
+                cudaGetLastError();
+            }
+        }
+        // agree: min over ranks
+        float okf = (float)ok;
+        float* dbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(d_ipc_.p) + (size_t)(nranks_ + 1) * sizeof(Rec));
+        MB_CUDA(cudaMemcpyAsync(dbuf, &okf, sizeof(float), cudaMemcpyHostToDevice, stream_));
+        MB_NCCL(g_nccl.AllReduce(dbuf, dbuf, 1, (ncclDataType_t)7 /* ncclFloat32 */, (ncclRedOp_t)3 /* ncclMin */, comm_, stream_));
+        MB_CUDA(cudaMemcpyAsync(&okf, dbuf, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        if (okf < 0.5f) {
+            void* keep = p2p_pos_base_;
+            p2p_close();
+            p2p_pos_base_ = keep;            // do not retry on every call
+            peer_pos_.assign(nranks_, nullptr);
+            return MB_OK;
+        }
+        p2p_ = true;
+        return MB_OK;
+    }
+    PeerComm* comm_of(int r) const { return reinterpret_cast<PeerComm*>(peer_comm_[r]); }
+    // distinct peers of a segment list, in first-appearance order
+    static void distinct_peers(const std::vector<DecompSeg>& v, std::vector<int>& out) {
+        out.clear();
+        for (auto& sg : v)
+            if (sg.count > 0 && std::find(out.begin(), out.end(), sg.peer) == out.end()) out.push_back(sg.peer);
+    }
+    PeerPush<T> make_push(unsigned long long epoch, bool with_data) const {
+        PeerPush<T> ps;
+        memset(&ps, 0, sizeof(ps));
+        ps.epoch = epoch;
+        std::vector<int> peers;
+        distinct_peers(halo_send_, peers);
+        if (with_data)
+            for (auto& sg : halo_send_) {
+                if (sg.count <= 0) continue;
+                ps.start[ps.n_seg] = sg.start;
+                ps.count[ps.n_seg] = sg.count;
+                ps.dst[ps.n_seg] = reinterpret_cast<T4*>(peer_pos_[sg.peer]);
+                ps.n_seg++;
+            }
+        for (int q : peers) {
+            ps.wait_flag[ps.n_peer] = &comm_of(rank_)->read_epoch[q];
+            ps.signal_flag[ps.n_peer] = &comm_of(q)->halo_epoch[rank_];
+            ps.n_peer++;
+        }
+        return ps;
+    }
+    PeerWait make_wait(unsigned long long epoch) const {
+        PeerWait w;
+        memset(&w, 0, sizeof(w));
+        w.epoch = epoch;
+        std::vector<int> peers;
+        distinct_peers(halo_recv_, peers);
+        for (int q : peers) w.flag[w.n++] = &comm_of(rank_)->halo_epoch[q];
+        return w;
+    }
+    PeerSignal make_signal(unsigned long long epoch, bool with_mom) const {
+        PeerSignal sg;
+        memset(&sg, 0, sizeof(sg));
+        sg.epoch = epoch;
+        std::vector<int> peers;
+        distinct_peers(halo_recv_, peers);
+        for (int q : peers) sg.read_flag[sg.n_peer++] = &comm_of(q)->read_epoch[rank_];
+        if (with_mom) {
+            const int par = (int)(epoch & 1ull);
+            sg.n_mom = nranks_;
+            for (int r = 0; r < nranks_; r++) {
+                sg.mom_dst[r] = comm_of(r)->mom[par][rank_];
+                sg.mom_flag[r] = &comm_of(r)->mom_epoch[par][rank_];
+            }
+        }
+        return sg;
+    }
+
     int comm_init(const void* uid, int rank, int nranks) override {
         if (nranks < 1 || rank < 0 || rank >= nranks || !uid) return set_error(MB_ERR_INVALID, "mb_comm_init: bad arguments");
         if (!g_nccl.load()) return set_error(MB_ERR_INVALID, "mb_comm_init: libnccl.so.2 could not be loaded");
+        p2p_close();
         if (comm_) { g_nccl.CommDestroy(comm_); comm_ = nullptr; }
         rank_ = rank;
         nranks_ = nranks;
@@ -1194,11 +1345,17 @@ class Engine : public EngineBase {
         const int vvb = std::max(1, std::min((n_own + VV_THREADS - 1) / VV_THREADS, 4 * sm_count_));  // grid-stride: <= 592 partials
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
+        // decomposed run over peer memory (peer.cuh): K1 mirrors the boundary slots into the neighbours while it drifts
+        const unsigned long long epoch = dec ? ++epoch_ : 0ull;
+        const bool p2p_halo = dec && p2p_active() && !host_rebuild_hint;  // rebuild steps all-gather the state instead
+        PeerPush<T> push;
+        memset(&push, 0, sizeof(push));
+        if (p2p_halo) push = make_push(epoch, true);
         prof_.begin(Prof::VV);
         vv_kick_drift_kernel<T><<<std::min(nb, 4 * sm_count_), 256, 0, stream_>>>(
             s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
             c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0, (dual_ && path_ == 1) ? d_xprune4_.as<T4>() : nullptr,
-            g_.skin_in_half2, handle_prune);
+            g_.skin_in_half2, handle_prune, push);
         prof_.end(Prof::VV);
         launches_++;
         if (clear_cm_after_k1) {
@@ -1242,6 +1399,9 @@ class Engine : public EngineBase {
                 MB_TRY(allgather_state());
                 MB_TRY(enqueue_rebuild(true, false));
                 MB_TRY(update_ownership());
+            } else if (p2p_halo) {
+                peer_wait_kernel<<<1, 32, 0, stream_>>>(make_wait(epoch));  // the neighbours' pushes of this epoch have landed
+                launches_++;
             } else {
                 MB_TRY(halo_exchange());
             }
@@ -1255,13 +1415,21 @@ class Engine : public EngineBase {
         if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
         else MB_TRY(launch_force(false, dec));
         MB_TRY(launch_bonded(false));
+        const bool p2p_sig = dec && p2p_active();  // (after a rebuild: the new ownership's peers)
+        PeerSignal sig;
+        memset(&sig, 0, sizeof(sig));
+        if (p2p_sig) sig = make_signal(epoch, do_cm_now != 0);
         prof_.begin(Prof::VV);
         vv_kick2_kernel<T><<<vvb2, VV_THREADS, 0, stream_>>>(s0b, n_ownb, c.dt_half, do_cm_now, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
                                                              d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0,
-                                                             dec ? d_mom_.as<double>() : nullptr);
+                                                             dec ? d_mom_.as<double>() : nullptr, sig);
         prof_.end(Prof::VV);
         launches_++;
-        if (dec && do_cm_now) {
+        if (p2p_sig && do_cm_now) {
+            // sum(m v) of all slabs arrived by peer stores: add them in rank order
+            peer_cm_kernel<T><<<1, 32, 0, stream_>>>(comm_of(rank_), nranks_, epoch, c.inv_mass, cm);
+            launches_++;
+        } else if (dec && do_cm_now) {
             // global sum(m v): one 24-byte all-reduce per step, then v_cm for the lazy subtraction
             MB_NCCL(g_nccl.AllReduce(d_mom_.as<double>(), d_mom_.as<double>() + 4, 3, ncclDouble, ncclSum, comm_, stream_));
             cm_from_sum_kernel<T><<<1, 1, 0, stream_>>>(d_mom_.as<double>() + 4, c.inv_mass, cm);
@@ -1407,7 +1575,8 @@ class Engine : public EngineBase {
         if (p->init_step == 0 && p->remove_cm_every != 0) {
             // remove_CM_motion! before the first force evaluation (simulators.jl:563): zero-length kick
             vv_kick2_kernel<T><<<vvb, VV_THREADS, 0, stream_>>>(0, (int)n_, (T)0, 1, c.inv_mass, d_f4_.as<T4>(), d_mass_.as<T>(),
-                                                                d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0, nullptr);
+                                                                d_vel4_.as<T4>(), d_partial_.as<double>(), ctl, cm, 0, nullptr,
+                                                                PeerSignal{});
             launches_++;
             cm_pending = true;
         }
@@ -1416,10 +1585,18 @@ class Engine : public EngineBase {
             // lists built from here on cover only the owned slab
             build_b0_ = own_b0_;
             build_nb_ = own_nb_;
+            MB_TRY(p2p_setup());  // collective; falls back to the NCCL transport on every rank if any mapping fails
         }
         if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
         else MB_TRY(launch_force(false, dec));
         MB_TRY(launch_bonded(false));
+        if (dec) {
+            const unsigned long long e0 = ++epoch_;  // this force evaluation read the replicated state: tell the pushers
+            if (p2p_active()) {
+                peer_signal_kernel<<<1, 32, 0, stream_>>>(make_signal(e0, false));
+                launches_++;
+            }
+        }
 
         // CUDA-graph path: static per-step sequence (remove_CM_motion in {0,1}, no stage timers requested)
         bool use_graph = graph_enabled_ && !graph_failed_ && !prof_.enabled && c.do_cm >= 0 && p->n_steps >= 4 &&
@@ -1531,6 +1708,7 @@ class Engine : public EngineBase {
         o->kernel_launches = launches_;
         o->graph_mode = graph_used_ ? 1 : (graph_failed_ ? -1 : 0);
         o->reserved_ = decomposed() ? auto_every_ : 0;
+        o->peer_transport = (decomposed() && p2p_active()) ? 1 : 0;
         prof_.collect();
         o->force_ms = prof_.ms[Prof::FORCE]; o->force_launches = prof_.count[Prof::FORCE];
         o->vv_ms = prof_.ms[Prof::VV]; o->vv_launches = prof_.count[Prof::VV];
@@ -1592,6 +1770,14 @@ class Engine : public EngineBase {
     std::vector<int> layer_start_;       // slot index of the first atom of every cell layer (ncz + 1)
     std::vector<DecompSeg> halo_send_, halo_recv_;
     DevBuf d_layer_start_, d_mom_;
+    // peer-memory transport (peer.cuh): IPC-mapped position arrays and PeerComm blocks of the other ranks
+    bool p2p_ = false;
+    void* p2p_pos_base_ = nullptr;            // the d_pos4_ allocation the peers have mapped
+    DevBuf d_comm_, d_ipc_;
+    std::vector<void*> peer_pos_, peer_comm_; // [rank]; own entries point at the local buffers
+    unsigned long long epoch_ = 0;            // force evaluations of decomposed runs (same on every rank)
+    bool plan_fits_ = false;
+    int plan_key_[3] = {-1, -1, -1};
     int64_t sp_n_[3] = {0, 0, 0};
     DevBuf d_sp_idx_k_[3], d_sp_par_k_[3], d_sp_partial_, d_sp_energy_;
     DevBuf d_mass_in_, d_charge_in_, d_ljp_in_;

@@ -9,6 +9,7 @@
 // is applied at every rebuild and on export, which is equivalent under the minimum-image convention.
 #pragma once
 #include "cells.cuh"
+#include "peer.cuh"
 
 namespace mb {
 
@@ -150,7 +151,11 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
                                      typename VT<T>::T4* __restrict__ vel4, int* __restrict__ flag, Control* __restrict__ ctl,
                                      cudaGraphConditionalHandle handle, int use_handle,
                                      const typename VT<T>::T4* __restrict__ xprune4, T skin_in_half2,
-                                     cudaGraphConditionalHandle handle_prune) {
+                                     cudaGraphConditionalHandle handle_prune, PeerPush<T> push) {
+    if (push.n_peer > 0) {  // decomposed run over peer memory: the neighbours must be done with the previous halo data
+        if ((int)threadIdx.x < push.n_peer) spin_until(push.wait_flag[threadIdx.x], push.epoch - 1);
+        __syncthreads();
+    }
     const bool cmv = cm->valid != 0;
     const T cx = cm->v[0], cy = cm->v[1], cz = cm->v[2];
     bool moved = false, moved_in = false;
@@ -167,6 +172,8 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
         p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
         vel4[s] = v;
         pos4[s] = p;
+        for (int q = 0; q < push.n_seg; q++)  // halo exchange fused into the drift: mirror boundary slots into the peers
+            if ((unsigned int)(s - push.start[q]) < (unsigned int)push.count[q]) push.dst[q][s] = p;
         const T dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
         const T d2 = dx * dx + dy * dy + dz * dz;
         moved |= (d2 > skin_half2);
@@ -183,6 +190,7 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
     __shared__ float s_d2[32];
     __shared__ bool s_last;
     if ((threadIdx.x & 31) == 0) s_d2[threadIdx.x >> 5] = d2max;
+    if (push.n_peer > 0) __threadfence_system();  // peer stores of this thread before the CTA's ticket
     __syncthreads();
     if (threadIdx.x == 0) {
         float m = 0.f;
@@ -203,6 +211,10 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
             cudaGraphSetConditional(handle, rb ? 1u : 0u);
             if (xprune4) cudaGraphSetConditional(handle_prune, (rb || *(volatile int*)&ctl->prune) ? 1u : 0u);
         }
+        if (push.n_peer > 0) {  // every CTA's peer stores are ordered before its ticket: publish the epoch
+            __threadfence_system();
+            for (int q = 0; q < push.n_peer; q++) st_release_sys(push.signal_flag[q], push.epoch);
+        }
     }
 }
 
@@ -215,7 +227,8 @@ template <typename T>
 __global__ void __launch_bounds__(VV_THREADS)
     vv_kick2_kernel(int s0, int n, T dt_half, int do_cm, double inv_total_mass, const typename VT<T>::T4* __restrict__ f4,
                     const T* __restrict__ mass, typename VT<T>::T4* __restrict__ vel4, double* __restrict__ partial,
-                    Control* __restrict__ ctl, CmState<T>* __restrict__ cm, int apply_pending, double* __restrict__ mom_out) {
+                    Control* __restrict__ ctl, CmState<T>* __restrict__ cm, int apply_pending, double* __restrict__ mom_out,
+                    PeerSignal sig) {
     double px = 0, py = 0, pz = 0;
     for (int s = s0 + blockIdx.x * blockDim.x + threadIdx.x; s < s0 + n; s += gridDim.x * blockDim.x) {
         typename VT<T>::T4 v = vel4[s];
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(VV_THREADS)
         const T m = mass[s];
         px += (double)(v.x * m); py += (double)(v.y * m); pz += (double)(v.z * m);
     }
-    if (!do_cm) return;
+    if (!do_cm && sig.n_peer == 0) return;
     __shared__ double s_red[VV_THREADS / 32][3];
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -269,7 +282,17 @@ __global__ void __launch_bounds__(VV_THREADS)
         if (tid == 0) {
             a = b = c = 0;
             for (int w = 0; w < VV_THREADS / 32; w++) { a += s_red[w][0]; b += s_red[w][1]; c += s_red[w][2]; }
-            if (mom_out) {  // decomposed run: publish this rank's sum(m v); the all-reduce and cm_from_sum_kernel finish it
+            // peer-memory transport: the force kernel in front of this one is done with the halo data ...
+            for (int q = 0; q < sig.n_peer; q++) st_release_sys(sig.read_flag[q], sig.epoch);
+            if (!do_cm) return;
+            if (sig.n_mom > 0) {  // ... and sum(m v) goes to every rank (peer_cm_kernel adds them in rank order)
+                for (int r = 0; r < sig.n_mom; r++) {
+                    volatile double* d = sig.mom_dst[r];
+                    d[0] = a; d[1] = b; d[2] = c;
+                }
+                __threadfence_system();
+                for (int r = 0; r < sig.n_mom; r++) st_release_sys(sig.mom_flag[r], sig.epoch);
+            } else if (mom_out) {  // decomposed run over NCCL: the all-reduce and cm_from_sum_kernel finish it
                 mom_out[0] = a; mom_out[1] = b; mom_out[2] = c;
             } else {
                 cm->v[0] = (T)(a * inv_total_mass);
@@ -287,6 +310,26 @@ __global__ void cm_from_sum_kernel(const double* __restrict__ mom_sum, double in
     cm->v[1] = (T)(mom_sum[1] * inv_total_mass);
     cm->v[2] = (T)(mom_sum[2] * inv_total_mass);
     cm->valid = 1;
+}
+
+// v_cm from the nranks partial sums of the peer-memory all-to-all, added in rank order (see peer.cuh)
+template <typename T>
+__global__ void peer_cm_kernel(const PeerComm* __restrict__ comm, int nranks, unsigned long long epoch, double inv_total_mass,
+                               CmState<T>* __restrict__ cm) {
+    const int par = (int)(epoch & 1ull);
+    if ((int)threadIdx.x < nranks) spin_until(&comm->mom_epoch[par][threadIdx.x], epoch);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int r = 0; r < nranks; r++) {
+            const volatile double* m = comm->mom[par][r];
+            a += m[0]; b += m[1]; c += m[2];
+        }
+        cm->v[0] = (T)(a * inv_total_mass);
+        cm->v[1] = (T)(b * inv_total_mass);
+        cm->v[2] = (T)(c * inv_total_mass);
+        cm->valid = 1;
+    }
 }
 
 // stand-alone momentum pass (remove_CM_motion! before the first step): same reduction, no kick

@@ -20,9 +20,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir, n_steps):
+def _worker(rank, world, port, out_dir, n_steps, p2p):
     import torch
     import torch.distributed as dist
+    os.environ["MOLLYB200_P2P"] = "1" if p2p else "0"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -39,29 +40,37 @@ def _worker(rank, world, port, out_dir, n_steps):
     mb.comm_init(s, uid[0], rank, world)
     mb.simulate(s, mb.VelocityVerlet(dt=0.002), n_steps)
     mb.simulate(s, mb.VelocityVerlet(dt=0.002), 15, init_step=n_steps)  # second call re-enters with a live list
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=s.coords, v=s.velocities, stats=np.array([s.stats()["n_rebuilds"]]))
+    st = s.stats()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=s.coords, v=s.velocities,
+             stats=np.array([st["n_rebuilds"], st["peer_transport"]]))
     s.close()
     dist.destroy_process_group()
 
 
-def test_decomposed_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("world,p2p", [(2, True), (2, False), (4, True)])
+def test_decomposed_matches_single_gpu(tmp_path, world, p2p):
+    """p2p=True: halo exchange + momentum sum over NVLink peer memory (peer.cuh); False: the NCCL transport."""
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     n_steps = 45
     sd = H.lj_fluid(16, seed=9, dtype=np.float64, temp=120.0)
     inter = (mb.LennardJones(cutoff=mb.ShiftedForceCutoff(1.0), use_neighbors=True),)
     ref = H.make_system(sd, inter, np.float64, r_list=1.15, n_steps=20)
     mb.simulate(ref, mb.VelocityVerlet(dt=0.002), n_steps)
     mb.simulate(ref, mb.VelocityVerlet(dt=0.002), 15, init_step=n_steps)
-    world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), n_steps), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), n_steps, p2p), nprocs=world, join=True)
     outs = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
     for o in outs:
         d = o["x"] - ref.coords
         d -= sd["box"] * np.round(d / sd["box"])
-        print("decomposed vs single: dx", np.abs(d).max(), "dv", np.abs(o["v"] - ref.velocities).max(), "rebuilds", o["stats"])
+        print(f"decomposed ({world} ranks, p2p requested {p2p}) vs single: dx", np.abs(d).max(), "dv",
+              np.abs(o["v"] - ref.velocities).max(), "rebuilds / peer_transport", o["stats"])
         assert np.abs(d).max() < 1e-9 and np.abs(o["v"] - ref.velocities).max() < 1e-8
-    assert np.array_equal(outs[0]["x"], outs[1]["x"]) and np.array_equal(outs[0]["v"], outs[1]["v"])
+    for o in outs[1:]:  # every rank returns the same whole system, and all ranks took the same transport
+        assert np.array_equal(outs[0]["x"], o["x"]) and np.array_equal(outs[0]["v"], o["v"])
+        assert o["stats"][1] == outs[0]["stats"][1]
+    if not p2p:
+        assert outs[0]["stats"][1] == 0
     ref.close()
