@@ -1157,6 +1157,8 @@ class Engine : public EngineBase {
         out.f4 = d_f4_.as<T4>();
         out.pe_partial = d_pe_partial_.as<double>();
         out.vir_partial = d_pe_partial_.as<double>() + g_.nbricks;
+        out.gate = gate_;  // one-shot: set by the decomposed step in front of this launch
+        memset(&gate_, 0, sizeof(gate_));
         switch (P_.coul_kind) {
             case COUL_NONE:
                 return P_.uniform_lj ? launch_force_c<COUL_NONE, true>(energy, out, b0, nbr) : launch_force_c<COUL_NONE, false>(energy, out, b0, nbr);
@@ -1338,7 +1340,7 @@ class Engine : public EngineBase {
     };
     int enqueue_step(const StepCfg& c, int do_cm_now, bool clear_cm_after_k1, bool capture,
                      cudaGraphConditionalHandle handle, cudaGraph_t graph, cudaGraph_t* body_out, bool host_rebuild_hint,
-                     cudaGraphConditionalHandle handle_prune = 0, cudaGraph_t* body_prune_out = nullptr) {
+                     cudaGraphConditionalHandle handle_prune = 0, cudaGraph_t* body_prune_out = nullptr, bool defer_cm = false) {
         const bool dec = decomposed() && path_ == 1;
         const int s0 = dec ? own_s0_ : 0, n_own = dec ? own_n_ : (int)n_;
         const int nb = std::max(1, (n_own + 255) / 256);
@@ -1351,6 +1353,13 @@ class Engine : public EngineBase {
         PeerPush<T> push;
         memset(&push, 0, sizeof(push));
         if (p2p_halo) push = make_push(epoch, true);
+        if (cm_deferred_epoch_) {  // the previous step left v_cm in the momentum all-to-all (no peer_cm_kernel)
+            push.cm_comm = comm_of(rank_);
+            push.cm_nranks = nranks_;
+            push.cm_epoch = cm_deferred_epoch_;
+            push.cm_inv_mass = c.inv_mass;
+            cm_deferred_epoch_ = 0;
+        }
         prof_.begin(Prof::VV);
         vv_kick_drift_kernel<T><<<std::min(nb, 4 * sm_count_), 256, 0, stream_>>>(
             s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
@@ -1400,8 +1409,7 @@ class Engine : public EngineBase {
                 MB_TRY(enqueue_rebuild(true, false));
                 MB_TRY(update_ownership());
             } else if (p2p_halo) {
-                peer_wait_kernel<<<1, 32, 0, stream_>>>(make_wait(epoch));  // the neighbours' pushes of this epoch have landed
-                launches_++;
+                gate_ = make_wait(epoch);  // the force kernel's CTAs wait for the neighbours' pushes of this epoch
             } else {
                 MB_TRY(halo_exchange());
             }
@@ -1425,7 +1433,9 @@ class Engine : public EngineBase {
                                                              dec ? d_mom_.as<double>() : nullptr, sig);
         prof_.end(Prof::VV);
         launches_++;
-        if (p2p_sig && do_cm_now) {
+        if (p2p_sig && do_cm_now && defer_cm && !c.thermostat) {
+            cm_deferred_epoch_ = epoch;  // the next step's K1 adds the slabs' sums itself
+        } else if (p2p_sig && do_cm_now) {
             // sum(m v) of all slabs arrived by peer stores: add them in rank order
             peer_cm_kernel<T><<<1, 32, 0, stream_>>>(comm_of(rank_), nranks_, epoch, c.inv_mass, cm);
             launches_++;
@@ -1571,6 +1581,7 @@ class Engine : public EngineBase {
                                     cudaMemcpyHostToDevice, stream_));
             MB_CUDA(cudaStreamSynchronize(stream_));  // t is a local
         }
+        cm_deferred_epoch_ = 0;
         bool cm_pending = false;  // host mirror of cm->valid
         if (p->init_step == 0 && p->remove_cm_every != 0) {
             // remove_CM_motion! before the first force evaluation (simulators.jl:563): zero-length kick
@@ -1623,7 +1634,7 @@ class Engine : public EngineBase {
                 const bool clear_after_k1 = cm_pending && !do_cm;  // K1 consumed v_cm; nothing overwrites it this step
                 const int every = (dec && rebuild_every_ == 0) ? auto_every_ : rebuild_every_;  // decomposed: fixed interval, adapted per call
                 const bool hint = every > 0 && k > 1 && (step_n - 1) % every == 0;
-                MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint));
+                MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint, 0, nullptr, /*defer_cm=*/k < p->n_steps));
                 cm_pending = (do_cm != 0) && !c.thermostat;
                 n_steps_++;
             }
@@ -1777,6 +1788,8 @@ class Engine : public EngineBase {
     std::vector<void*> peer_pos_, peer_comm_; // [rank]; own entries point at the local buffers
     unsigned long long epoch_ = 0;            // force evaluations of decomposed runs (same on every rank)
     bool plan_fits_ = false;
+    PeerWait gate_ = {};
+    unsigned long long cm_deferred_epoch_ = 0;
     int plan_key_[3] = {-1, -1, -1};
     int64_t sp_n_[3] = {0, 0, 0};
     DevBuf d_sp_idx_k_[3], d_sp_par_k_[3], d_sp_partial_, d_sp_energy_;

@@ -15,6 +15,7 @@
 #pragma once
 #include "cells.cuh"
 #include "pair.cuh"
+#include "peer.cuh"
 
 namespace mb {
 
@@ -34,6 +35,7 @@ struct ForceOut {
     typename VT<T>::T4* f4;   // per-slot force (w unused)
     double* pe_partial;       // [nbricks] (ENERGY)
     double* vir_partial;      // [nbricks*6] xx,yy,zz,xy,xz,yz (ENERGY)
+    PeerWait gate;            // decomposed run over peer memory: epoch flags the halo data of this step arrives under
 };
 
 template <typename T, int COUL, bool UNIFORM, bool SHIFT, bool ENERGY, int LPA>
@@ -55,6 +57,11 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
             for (int k = 0; k < 6; k++) out.vir_partial[(size_t)b * 6 + k] = 0.0;
         }
         return;
+    }
+    if (out.gate.n > 0) {  // the neighbours' drift kernels store this step's halo positions into pos4 (peer.cuh)
+        if (tid < out.gate.n) spin_until(out.gate.flag[tid], out.gate.epoch);
+        __syncthreads();
+        fence_proxy_async_all();  // the TMA engine reads them next
     }
     T4* s_pos = reinterpret_cast<T4*>(smem_raw);
     T2* s_lj = reinterpret_cast<T2*>(s_pos + g.halo_cap);

@@ -14,7 +14,9 @@
 //   wait(e)  spins until halo_epoch[q] >= e for every peer q that pushes to me.
 //   force(e), K2(e): K2's last CTA sets  peer.read_epoch[me] = e  for every q that pushes to me, and (CM removal)
 //            writes sum(m v) into every rank's mom[e&1][me] followed by mom_epoch[e&1][me] = e.
-//   cm(e)    spins until mom_epoch[e&1][r] >= e for all r, adds the nranks partial sums in rank order.
+//   cm(e)    spins until mom_epoch[e&1][r] >= e for all r, adds the nranks partial sums in rank order: done by every
+//            CTA of K1(e+1) itself between two steps, by peer_cm_kernel when something else consumes v_cm next.
+//   The force kernel's CTAs do wait(e) themselves (ForceOut::gate), so a non-rebuild step is K1 -> force -> K2.
 // All waits are bounded (a few seconds of %globaltimer) and trap instead of hanging the GPU.
 #pragma once
 #include "common.cuh"
@@ -65,6 +67,11 @@ struct PeerPush {
     const unsigned long long* wait_flag[MB_MAX_SEG];  // my comm->read_epoch[peer]
     unsigned long long* signal_flag[MB_MAX_SEG];      // peer comm->halo_epoch[me]
     unsigned long long epoch;                          // waits need epoch-1, signals write epoch
+    // v_cm of the previous step straight from the momentum all-to-all (replaces peer_cm_kernel between two steps)
+    const PeerComm* cm_comm;
+    int cm_nranks;                                     // 0: take v_cm from CmState as usual
+    unsigned long long cm_epoch;
+    double cm_inv_mass;
 };
 
 // K2 argument: read-done signals and the momentum all-to-all

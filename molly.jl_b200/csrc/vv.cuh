@@ -152,12 +152,31 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
                                      cudaGraphConditionalHandle handle, int use_handle,
                                      const typename VT<T>::T4* __restrict__ xprune4, T skin_in_half2,
                                      cudaGraphConditionalHandle handle_prune, PeerPush<T> push) {
-    if (push.n_peer > 0) {  // decomposed run over peer memory: the neighbours must be done with the previous halo data
+    bool cmv = cm->valid != 0;
+    T cx = cm->v[0], cy = cm->v[1], cz = cm->v[2];
+    if (push.n_peer > 0 || push.cm_nranks > 0) {  // decomposed run over peer memory (peer.cuh)
+        __shared__ double s_cm[3];
+        // the neighbours must be done with the previous halo data before it is overwritten ...
         if ((int)threadIdx.x < push.n_peer) spin_until(push.wait_flag[threadIdx.x], push.epoch - 1);
+        // ... and v_cm of the previous step is the rank-ordered sum of what every rank's K2 stored here
+        const int par = (int)(push.cm_epoch & 1ull);
+        const int r = (int)threadIdx.x - 32;
+        if (r >= 0 && r < push.cm_nranks) spin_until(&push.cm_comm->mom_epoch[par][r], push.cm_epoch);
         __syncthreads();
+        if (push.cm_nranks > 0) {
+            if (threadIdx.x == 0) {
+                double a = 0, b = 0, c = 0;
+                for (int q = 0; q < push.cm_nranks; q++) {
+                    const volatile double* m = push.cm_comm->mom[par][q];
+                    a += m[0]; b += m[1]; c += m[2];
+                }
+                s_cm[0] = a * push.cm_inv_mass; s_cm[1] = b * push.cm_inv_mass; s_cm[2] = c * push.cm_inv_mass;
+            }
+            __syncthreads();
+            cmv = true;
+            cx = (T)s_cm[0]; cy = (T)s_cm[1]; cz = (T)s_cm[2];
+        }
     }
-    const bool cmv = cm->valid != 0;
-    const T cx = cm->v[0], cy = cm->v[1], cz = cm->v[2];
     bool moved = false, moved_in = false;
     float d2max = 0.f;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -190,13 +209,15 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
     __shared__ float s_d2[32];
     __shared__ bool s_last;
     if ((threadIdx.x & 31) == 0) s_d2[threadIdx.x >> 5] = d2max;
-    if (push.n_peer > 0) __threadfence_system();  // peer stores of this thread before the CTA's ticket
     __syncthreads();
     if (threadIdx.x == 0) {
         float m = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s_d2[w]);
         if (m > 0.f) atomicMax(&ctl->max_disp2_bits, __float_as_uint(m));  // one atomic per CTA
-        __threadfence();
+        // the CTA barrier above ordered every thread's stores before this fence (cumulativity); at system scope when
+        // some of them went to a peer GPU
+        if (push.n_peer > 0) __threadfence_system();
+        else __threadfence();
         unsigned int t = atomicInc(&ctl->ticket, gridDim.x - 1);
         s_last = (t == gridDim.x - 1);
     }
