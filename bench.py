@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cm", action="store_true", help="diagnostic: remove_CM_motion=false")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of the spatial decomposition")
     args = ap.parse_args()
 
@@ -249,7 +250,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         mb.comm_init(sysm, uid[0], rank, world)
     coupling = mb.AndersenThermostat(300.0, 1.0) if wl == "c3" else None  # config 3: VelocityVerlet + Andersen
-    sim = mb.VelocityVerlet(dt=dt, coupling=coupling, remove_CM_motion=1)
+    sim = mb.VelocityVerlet(dt=dt, coupling=coupling, remove_CM_motion=0 if args.no_cm else 1)
     rng = np.random.default_rng(1234 + rank)
 
     def barrier():

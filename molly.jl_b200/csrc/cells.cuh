@@ -102,45 +102,43 @@ __global__ void bin_count_kernel(const Control* __restrict__ ctl, Geom<T> g, typ
 }
 
 // ---- R2: exclusive scan of cell counts (single CTA) --------------------------------------------
+// Every thread owns a contiguous chunk of cells: chunk sums -> one block-wide scan of the 1024 sums -> chunk
+// prefixes. Two barriers in total (the cell count is ~45 k at C2; a tile-by-tile scan with a carried sum cost
+// four barriers per 1024 cells and 45 us).
 __global__ void cell_scan_kernel(const Control* __restrict__ ctl, int ncells, int n, const int* __restrict__ cell_count,
                                  int* __restrict__ cell_start, int* __restrict__ cell_fill) {
     if (!ctl->rebuild) return;
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    if (tid == 0) s_carry = 0;
+    const int per = (ncells + blockDim.x - 1) / blockDim.x;
+    const int c0 = min(tid * per, ncells), c1 = min(c0 + per, ncells);
+    int sum = 0;
+    for (int c = c0; c < c1; c++) sum += cell_count[c];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    for (int base = 0; base < ncells; base += blockDim.x) {
-        int c = base + tid;
-        int v = (c < ncells) ? cell_count[c] : 0;
-        int incl = v;
+    if (wid == 0) {
+        int w = (lane < nw) ? s_warp[lane] : 0;
+        int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
         }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            int w = (lane < nw) ? s_warp[lane] : 0;
-            int wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            s_warp[lane] = wi - w;  // exclusive warp offsets
-        }
-        __syncthreads();
-        int carry = s_carry;
-        int excl = carry + s_warp[wid] + incl - v;
-        if (c < ncells) {
-            cell_start[c] = excl;
-            cell_fill[c] = 0;
-        }
-        __syncthreads();
-        if (tid == blockDim.x - 1) s_carry = excl + v;
-        __syncthreads();
+        s_warp[lane] = wi - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    int run = s_warp[wid] + incl - sum;
+    for (int c = c0; c < c1; c++) {
+        const int v = cell_count[c];
+        cell_start[c] = run;
+        cell_fill[c] = 0;
+        run += v;
     }
     if (tid == 0) cell_start[ncells] = n;
 }
