@@ -102,25 +102,23 @@ __global__ void bin_count_kernel(const Control* __restrict__ ctl, Geom<T> g, typ
 }
 
 // ---- R2: exclusive scan of cell counts (single CTA) --------------------------------------------
-// Every thread owns a contiguous chunk of cells: chunk sums -> one block-wide scan of the 1024 sums -> chunk
-// prefixes. Two barriers in total (the cell count is ~45 k at C2; a tile-by-tile scan with a carried sum cost
-// four barriers per 1024 cells and 45 us).
+// Every warp owns a contiguous chunk of cells and walks it in coalesced tiles of 32: chunk sums (lanes accumulate
+// independently, one warp reduction) -> scan of the 32 chunk sums -> tile-by-tile shuffle scan with a register carry.
+// Two block barriers in total (a tile-by-tile scan across the whole CTA cost four barriers per 1024 cells, 45 us at
+// C2's 45 k cells).
 __global__ void cell_scan_kernel(const Control* __restrict__ ctl, int ncells, int n, const int* __restrict__ cell_count,
                                  int* __restrict__ cell_start, int* __restrict__ cell_fill) {
     if (!ctl->rebuild) return;
     __shared__ int s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    const int per = (ncells + blockDim.x - 1) / blockDim.x;
-    const int c0 = min(tid * per, ncells), c1 = min(c0 + per, ncells);
+    const int per = (((ncells + nw - 1) / nw) + 31) & ~31;  // cells per warp, whole tiles
+    const int c0 = min(wid * per, ncells), c1 = min(c0 + per, ncells);
     int sum = 0;
-    for (int c = c0; c < c1; c++) sum += cell_count[c];
-    int incl = sum;
+#pragma unroll 4
+    for (int c = c0 + lane; c < c1; c += 32) sum += cell_count[c];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[wid] = incl;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_warp[wid] = sum;
     __syncthreads();
     if (wid == 0) {
         int w = (lane < nw) ? s_warp[lane] : 0;
@@ -130,15 +128,24 @@ __global__ void cell_scan_kernel(const Control* __restrict__ ctl, int ncells, in
             int t = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= o) wi += t;
         }
-        s_warp[lane] = wi - w;  // exclusive warp offsets
+        s_warp[lane] = wi - w;  // exclusive chunk offsets
     }
     __syncthreads();
-    int run = s_warp[wid] + incl - sum;
-    for (int c = c0; c < c1; c++) {
-        const int v = cell_count[c];
-        cell_start[c] = run;
-        cell_fill[c] = 0;
-        run += v;
+    int carry = s_warp[wid];
+    for (int base = c0; base < c1; base += 32) {
+        const int c = base + lane;
+        const int v = (c < c1) ? cell_count[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (c < c1) {
+            cell_start[c] = carry + incl - v;
+            cell_fill[c] = 0;
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (tid == 0) cell_start[ncells] = n;
 }
