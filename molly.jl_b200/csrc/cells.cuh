@@ -411,16 +411,23 @@ __device__ __forceinline__ void stage_halo_wait(const Geom<T>& g, int b, const B
         __syncthreads();
         return;
     }
-    // brick-local frame
-    int B[3] = {b % g.nb[0], (b / g.nb[0]) % g.nb[1], b / (g.nb[0] * g.nb[1])};
-    double org[3];
+    // The list builder works in a brick-local frame (ALWAYS_LOCALIZE: origin = brick corner, its row trimming needs
+    // coordinates relative to the brick). The force kernel only needs every staged atom in the SAME frame as the owned
+    // atoms, so it keeps global coordinates and moves just the runs that are periodic images by +-L (in double, one
+    // rounding) - a fifth of a boundary brick's halo instead of all of it.
+    double org[3] = {0.0, 0.0, 0.0};
+    if (ALWAYS_LOCALIZE) {
+        int B[3] = {b % g.nb[0], (b / g.nb[0]) % g.nb[1], b / (g.nb[0] * g.nb[1])};
 #pragma unroll
-    for (int d = 0; d < 3; d++) org[d] = (double)(B[d] * g.b[d]) * g.celld[d];
+        for (int d = 0; d < 3; d++) org[d] = (double)(B[d] * g.b[d]) * g.celld[d];
+    }
+    constexpr int NO_SHIFT = 1 | (1 << 2) | (1 << 4);
     // 8-lane groups, one run each (a run is ~40 atoms): four runs per warp instruction
     const int l8 = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
     for (int r = grp; r < g.max_runs; r += ngrp) {
         Run run = my_runs[r];
         if (run.count <= 0) continue;
+        if (!ALWAYS_LOCALIZE && run.shift == NO_SHIFT) continue;
         const double ox = (double)((run.shift & 3) - 1) * g.Ld[0] - org[0];
         const double oy = (double)(((run.shift >> 2) & 3) - 1) * g.Ld[1] - org[1];
         const double oz = (double)(((run.shift >> 4) & 3) - 1) * g.Ld[2] - org[2];
@@ -442,6 +449,11 @@ __device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickH
     stage_halo_issue<T, WITH_LJ>(g, hd, my_runs, pos4, lj2, s_pos, s_lj, bar);
     stage_halo_wait<T, ALWAYS_LOCALIZE>(g, b, hd, my_runs, s_pos, bar);
 }
+
+// Main-list entries are stored as halo index << LIST_SHIFT (= byte offset of a float4 position in shared memory): the
+// force kernel saves a shift per entry. 16-bit entries therefore address at most LIST_MAX_HALO staged atoms per brick.
+constexpr int LIST_SHIFT = 4;
+constexpr int LIST_MAX_HALO = 65536 >> LIST_SHIFT;
 
 // ---- R6: full-shell neighbour lists --------------------------------------------------------------
 // One CTA per brick, one warp per owned atom. Entries are 16-bit halo indices written in the lane-
@@ -595,7 +607,7 @@ __global__ void __launch_bounds__(256)
                         int m = count + __popc(mb_ & lt);
                         if (m < g.stride) {
                             int phys = (m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3);
-                            my_list[phys] = (unsigned short)c;
+                            my_list[phys] = (unsigned short)(c << LIST_SHIFT);
                         }
                     }
                     if (spec_hit) {
@@ -690,7 +702,7 @@ __global__ void __launch_bounds__(256)
             const int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
 #pragma unroll
             for (int e = 0; e < 4; e++) {  // logical entry index inside the group = l + 8 e
-                const T4 pj = s_pos[j[e]];
+                const T4 pj = s_pos[j[e] >> LIST_SHIFT];
                 const T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 const bool in = (dx * dx + dy * dy + dz * dz) <= g.rinner2;
                 const unsigned int bal = (__ballot_sync(sub_mask, in) >> (8 * (sub & 3))) & 0xffu;

@@ -119,6 +119,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// position record (x, y, z, q) at a 32-bit shared-memory address: explicit ld.shared, so the address is a plain
+// register + uniform base instead of a generic pointer that is converted at every use
+__device__ __forceinline__ float4 lds_pos(uint32_t addr, float) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ dbl4 lds_pos(uint32_t addr, double) {
+    dbl4 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.z), "=d"(r.w) : "r"(addr + 16u));
+    return r;
+}
+
 // streaming (read-once) global loads that do not pollute L1
 __device__ __forceinline__ uint2 ldg_stream_u2(const uint2* p) {
     uint2 r;

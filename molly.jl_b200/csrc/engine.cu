@@ -597,7 +597,7 @@ class Engine : public EngineBase {
                         if (nranks_ > 1 && bz != 1) continue;  // slabs are whole cell layers
                         double halo = (bx + 4.0) * (by + 4.0) * (bz + 4.0) * rho_c * 1.25 + 64;
                         double smem = halo * bytes_per_atom;
-                        if (smem > smem_budget || halo > 60000) continue;
+                        if (smem > smem_budget || halo * 1.1 + 96 > LIST_MAX_HALO) continue;
                         double occ = std::min(8.0, std::floor(smem_budget / smem));
                         // latency hiding improves with resident CTAs (8 warps each): measured shape, saturating at ~6
                         static const double eff_tab[9] = {0.0, 0.35, 0.55, 0.70, 0.80, 0.88, 0.95, 0.97, 1.0};
@@ -1077,9 +1077,9 @@ class Engine : public EngineBase {
             MB_TRY(read_ctl(c));
             int cap = (int)(c.max_halo * (1.0 + 0.08 * cap_scale_)) + 32;  // temporal drift of the fullest brick's halo
             cap = (cap + 63) & ~63;
-            g_.halo_cap = std::min(cap, 65535);
+            g_.halo_cap = std::min(cap, LIST_MAX_HALO);
             size_t need = std::max(force_smem_bytes() + 2048, build_smem_bytes() + 1024);
-            if (c.max_halo >= 65000 || need > smem_optin_) {
+            if (cap > LIST_MAX_HALO || need > smem_optin_) {  // list entries are 16-bit byte offsets of float4 records
                 // shrink the brick and retry
                 int* ub = user_b_;
                 int cur[3] = {g_.b[0], g_.b[1], g_.b[2]};

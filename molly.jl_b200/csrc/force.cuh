@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
     }
     T4* s_pos = reinterpret_cast<T4*>(smem_raw);
     T2* s_lj = reinterpret_cast<T2*>(s_pos + g.halo_cap);
+    uint32_t s_pos_u32 = smem_u32(s_pos);
+    asm volatile("" : "+r"(s_pos_u32));  // keep it in a register (otherwise the 5-instruction window-base computation is redone per group)
     __shared__ uint64_t s_bar;
     __shared__ IRow s_rows[64];
     const Run* my_runs = runs + (size_t)b * g.max_runs;
@@ -80,13 +82,39 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
     // evaluated, and those of the first task while the halo is still landing, so the global-memory latency of the
     // neighbour-list stream is off the critical path (each CTA only runs ~4 tasks per lane group).
     constexpr int LIST_HALF = (MB_LIST_BATCH >= 2) ? MB_LIST_BATCH / 2 : 1;
-    auto locate = [&](int task, int& slot, int& si) -> bool {
-        const bool valid = task < hd.i_count;
+    // task -> (slot, shared-memory index): the row search is done once per owned atom into a table instead of once per
+    // lane group and iteration (it was 5 % of the kernel's instructions)
+    constexpr int MAX_TASKS = 512;
+    __shared__ int2 s_task[MAX_TASKS];
+    auto search = [&](int task, int& slot, int& si) {
         int q = 0;
         while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
         const IRow row = s_rows[q];
-        slot = valid ? row.slot_begin + (task - row.cum) : 0;
-        si = valid ? row.smem_begin + (task - row.cum) : 0;
+        slot = row.slot_begin + (task - row.cum);
+        si = row.smem_begin + (task - row.cum);
+    };
+    const bool tabled = hd.i_count <= MAX_TASKS;
+    if (tabled) {
+        for (int t = tid; t < hd.i_count; t += blockDim.x) {  // s_rows is visible: stage_halo_issue synchronised the CTA
+            int sl, sm;
+            search(t, sl, sm);
+            s_task[t] = make_int2(sl, sm);
+        }
+        __syncthreads();
+    }
+    auto locate = [&](int task, int& slot, int& si) -> bool {
+        const bool valid = task < hd.i_count;
+        slot = 0;
+        si = 0;
+        if (valid) {
+            if (tabled) {
+                const int2 t = s_task[task];
+                slot = t.x;
+                si = t.y;
+            } else {
+                search(task, slot, si);
+            }
+        }
         return valid;
     };
     const int words_in_row = g.stride >> 5;  // groups a row can hold
@@ -146,23 +174,18 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
             fx += __uint_as_float((w.x ^ w.y) & 0x3f000000u);
             return;
 #endif
+            // entries are byte offsets of float4 records (halo index << LIST_SHIFT)
             int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
 #if defined(MB_ABL) && MB_ABL == 2  // ablation: arithmetic without the shared-memory gathers
-            j[0] = j[1] = j[2] = j[3] = (int)(threadIdx.x & 7);
-#endif
-#if defined(MB_ABL) && MB_ABL == 3  // ablation: shared-memory gathers without the arithmetic
-            {
-                const T4 a0 = s_pos[j[0]], a1 = s_pos[j[1]], a2 = s_pos[j[2]], a3 = s_pos[j[3]];
-                fx += a0.x + a1.x + a2.x + a3.x;
-                return;
-            }
+            j[0] = j[1] = j[2] = j[3] = (int)(threadIdx.x & 7) << LIST_SHIFT;
 #endif
             T4 pj[4];
             T2 lj[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                pj[u] = s_pos[j[u]];
-                if (!UNIFORM) lj[u] = s_lj[j[u]];
+                pj[u] = lds_pos(s_pos_u32 + (uint32_t)j[u] * (uint32_t)(sizeof(T4) >> LIST_SHIFT), (T)0);
+                if (!UNIFORM)
+                    lj[u] = *reinterpret_cast<const T2*>(reinterpret_cast<const char*>(s_lj) + (((size_t)j[u] * sizeof(T2)) >> LIST_SHIFT));
             }
 #if MB_USE_F32X2
             if constexpr (std::is_same<T, float>::value && UNIFORM && !SHIFT && !ENERGY && COUL == COUL_NONE) {
@@ -170,10 +193,11 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
 #pragma unroll
                 for (int h2 = 0; h2 < 2; h2++) {
                     const float4 a = pj[2 * h2], b = pj[2 * h2 + 1];
-                    const float2 one_m = make_float2(-1.f, -1.f);
-                    const float2 dx = __ffma2_rn(make_float2(a.x, b.x), one_m, make_float2(pi.x, pi.x));
-                    const float2 dy = __ffma2_rn(make_float2(a.y, b.y), one_m, make_float2(pi.y, pi.y));
-                    const float2 dz = __ffma2_rn(make_float2(a.z, b.z), one_m, make_float2(pi.z, pi.z));
+                    // scalar subtractions write straight into register pairs; packing (a.x, b.x) first costs two moves
+                    // per component because the gathered float4s arrive as x,y,z,w quads
+                    const float2 dx = make_float2(pi.x - a.x, pi.x - b.x);
+                    const float2 dy = make_float2(pi.y - a.y, pi.y - b.y);
+                    const float2 dz = make_float2(pi.z - a.z, pi.z - b.z);
                     const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
                     const float2 iv = make_float2(frcp(r2.x), frcp(r2.y));
                     const float2 i3 = __fmul2_rn(__fmul2_rn(iv, iv), iv);
@@ -256,7 +280,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
             for (int gi = 0; gi < n_groups; gi++) {
                 for (int m = l; m < 32; m += LPA) {
                     int phys = ((m & 7) << 2) + (m >> 3);
-                    eval((int)lp[gi * 32 + phys], std::false_type{});
+                    eval((int)lp[gi * 32 + phys] >> LIST_SHIFT, std::false_type{});
                 }
             }
         }
