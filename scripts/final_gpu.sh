@@ -12,7 +12,7 @@ for w in c2 c3; do
 done
 MOLLYB200_NO_GRAPH=1 ncu --set full --import-source on --clock-control none -k regex:brick_force_kernel -s 5 -c 1 -f -o gpurun_out/force_c2 \
   python bench.py --steps 12 --warmup 4 --no-e2e --no-cpu-baseline > gpurun_out/ncu_force.log 2>&1
-MOLLYB200_NO_GRAPH=1 ncu --set full --import-source on --clock-control none -k regex:build_lists_kernel -s 3 -c 1 -f -o gpurun_out/build_c2 \
+MOLLYB200_NO_GRAPH=1 ncu --set full --import-source on --clock-control none -k regex:build_lists_kernel -s 1 -c 1 -f -o gpurun_out/build_c2 \
   python bench.py --steps 12 --warmup 4 --no-e2e --no-cpu-baseline > gpurun_out/ncu_build.log 2>&1
 python - <<'PY'
 import json
