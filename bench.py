@@ -156,14 +156,27 @@ def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32):
         t = time.perf_counter() - t0
         return steps / t, o.max_threads(), t
     orc = H.make_oracle(sd, ointers, dtype=dtype)
-    nt = o.max_threads()
-    x, v = sd["coords"].astype(dtype), sd["velocities"].astype(dtype)
-    if warmup > 0:
-        x, v, _ = orc.simulate_vv(x, v, dt, warmup, remove_cm_every=1, r_list=rc + 0.2, nl_every=10, n_threads=nt)
-    t0 = time.perf_counter()
-    orc.simulate_vv(x, v, dt, steps, remove_cm_every=1, r_list=rc + 0.2, nl_every=10, n_threads=nt)
-    t = time.perf_counter() - t0
-    return steps / t, nt, t
+    # "all the host threads it can use": one thread per logical CPU is often slower than one per physical core for this
+    # memory-bound loop, so both are timed on the same sample and the faster one is reported
+    cands = {o.max_threads()}
+    try:
+        import psutil
+        phys, logical = psutil.cpu_count(logical=False), psutil.cpu_count(logical=True)
+        cands |= {c for c in (phys, logical) if c}
+    except Exception:
+        pass
+    best = None
+    x0, v0 = sd["coords"].astype(dtype), sd["velocities"].astype(dtype)
+    for nt in sorted(cands):
+        x, v = x0, v0
+        if warmup > 0:
+            x, v, _ = orc.simulate_vv(x, v, dt, warmup, remove_cm_every=1, r_list=rc + 0.2, nl_every=10, n_threads=nt)
+        t0 = time.perf_counter()
+        orc.simulate_vv(x, v, dt, steps, remove_cm_every=1, r_list=rc + 0.2, nl_every=10, n_threads=nt)
+        t = time.perf_counter() - t0
+        if best is None or steps / t > best[0]:
+            best = (steps / t, nt, t)
+    return best
 
 
 def main():
