@@ -572,7 +572,9 @@ class Engine : public EngineBase {
             const char* du = getenv("MOLLYB200_DUAL");
             const char* fr = getenv("MOLLYB200_INNER_SKIN_FRAC");
             if (fr) inner_frac_ = std::min(1.0, std::max(0.05, atof(fr)));
-            dual_ = (du && du[0] == '1') && !decomposed() && skin_ > 1e-6 && inner_frac_ < 0.999;
+            (void)du;
+            dual_ = false;  // measured and rejected (profiles/r01_experiments.md §2); the path is kept for reference but is no
+                            // longer selectable: it has not been re-validated since list entries became byte offsets
             const double skin_in = dual_ ? skin_ * inner_frac_ : skin_;
             const double r_in = dual_ ? max_rc_ + skin_in : r_list_;
             g.rinner2 = (T)(r_in * r_in);
