@@ -166,11 +166,70 @@ function Molly.pairwise_pe_loop_gpu!(pe_vec_nounits, buffers, sys::System{3, <:C
     return pe_vec_nounits
 end
 
+# ---- specific (bonded) interaction lists -> mb_set_specific ----------------------------------------------
+# InteractionList{2,3,4}Atoms of HarmonicBond / HarmonicAngle / PeriodicTorsion (src/types.jl:89-157). Anything else
+# makes simulate! fall through to the stock path. A torsion with several Fourier terms becomes one entry per term
+# (zero-k padding terms are dropped), like src/interactions/periodic_torsion.jl:100-142 sums them.
+function specific_desc(sil::InteractionList2Atoms)
+    inters = Array(sil.inters)
+    eltype(inters) <: HarmonicBond || return nothing
+    idx = Int32.(vcat(Array(sil.is)', Array(sil.js)'))                       # 2 x n, 1-based, column = one term
+    par = Float64.(vcat([ustrip(b.k) for b in inters]', [ustrip(b.r0) for b in inters]'))
+    return (0, idx, par)
+end
+function specific_desc(sil::InteractionList3Atoms)
+    inters = Array(sil.inters)
+    eltype(inters) <: HarmonicAngle || return nothing
+    idx = Int32.(vcat(Array(sil.is)', Array(sil.js)', Array(sil.ks)'))
+    par = Float64.(vcat([ustrip(a.k) for a in inters]', [ustrip(a.θ0) for a in inters]'))
+    return (1, idx, par)
+end
+function specific_desc(sil::InteractionList4Atoms)
+    inters = Array(sil.inters)
+    eltype(inters) <: PeriodicTorsion || return nothing
+    is, js, ks, ls = Array(sil.is), Array(sil.js), Array(sil.ks), Array(sil.ls)
+    idx, par = Int32[], Float64[]
+    for (t, tor) in enumerate(inters), m in eachindex(tor.periodicities)
+        k = Float64(ustrip(tor.ks[m]))
+        k == 0 && continue
+        append!(idx, (is[t], js[t], ks[t], ls[t]))
+        append!(par, (Float64(tor.periodicities[m]), Float64(ustrip(tor.phases[m])), k))
+    end
+    return (2, reshape(idx, 4, :), reshape(par, 3, :))
+end
+specific_desc(::Any) = nothing
+
+function set_specific!(ctx::Context, sys)
+    descs = map(specific_desc, sys.specific_inter_lists)
+    any(isnothing, descs) && return false
+    for (kind, idx, par) in descs     # at most one list per kind (the engine replaces a kind's list on every call)
+        check(ccall((:mb_set_specific, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int32}, Ptr{Float64}),
+                    ctx.handle, kind, size(idx, 2), idx, par))
+    end
+    return true
+end
+
+# ---- multi-GPU: one Julia process per GPU (MPI.jl / Distributed); the reference has nothing here -----------
+# rank 0: id = comm_unique_id(); broadcast the 128 bytes; every rank: comm_init!(sys, id, rank, nranks).
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:mb_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    return id
+end
+function comm_init!(sys::System{3, <:CuArray}, id::Vector{UInt8}, rank::Integer, nranks::Integer)
+    descs = engine_eligible(sys, sys.pairwise_inters)
+    isnothing(descs) && error("mollyb200: System is not engine-eligible")
+    ctx = context_for(sys, descs)
+    check(ccall((:mb_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), ctx.handle, id, rank, nranks))
+    return sys
+end
+
 # ---- simulate!(sys, ::VelocityVerlet, n) ----------------------------------------------------------------
 # Taken over only when nothing but the pairwise path contributes forces and nothing has to run on the host
 # every step; loggers fire between chunks of gcd(logger n_steps) steps (SURVEY.md Appendix A.11).
 function takeover_params(sys, sim::VelocityVerlet, n_steps, init_step, rng)
-    length(sys.specific_inter_lists) == 0 && length(sys.general_inters) == 0 || return nothing
+    length(sys.general_inters) == 0 || return nothing
+    all(!isnothing, map(specific_desc, sys.specific_inter_lists)) || return nothing
     kT, prob = 0.0, 0.0
     couplings = sim.coupling isa Tuple ? sim.coupling : (sim.coupling,)
     for c in couplings
@@ -192,6 +251,7 @@ function Molly.simulate!(sys::System{3, <:CuArray, T}, sim::VelocityVerlet, n_st
                       init_step=init_step, rng=rng, run_loggers=run_loggers, kwargs...)
     end
     ctx = context_for(sys, descs)
+    set_specific!(ctx, sys)
     chunk = run_loggers == false || isempty(sys.loggers) ? n_steps :
             max(1, reduce(gcd, (l.n_steps for l in values(sys.loggers))))
     done = 0
