@@ -34,7 +34,8 @@ def main():
     )
     for key in ("bond_idx", "bond_par", "angle_idx", "angle_par", "proper_idx", "proper_par", "improper_idx", "improper_par"):
         out[key] = top[key]
-    for name in ("lj_only", "coul_only", "bond_only", "angle_only", "proptor_only", "improptor_only", "all_cut"):
+    for name in ("lj_only", "coul_only", "bond_only", "angle_only", "proptor_only", "improptor_only", "all_cut",
+                 "all_pme_exact", "all_pme"):
         out[f"forces_{name}"] = np.loadtxt(f"{amber}/forces_{name}.txt")
         out[f"energy_{name}"] = np.float64(open(f"{amber}/energy_{name}.txt").read())
     np.savez_compressed(os.path.join(OUT, "6mrr.npz"), **out)

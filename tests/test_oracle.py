@@ -181,3 +181,25 @@ def test_6mrr_all_cut_openmm_golden(golden_6mrr):
     e += eb + o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
     assert np.linalg.norm(f + fb - g["forces_all_cut"], axis=1).max() < 1e-7
     assert abs(e - float(g["energy_all_cut"])) < 1e-5
+
+
+def test_6mrr_all_pme_openmm_golden(golden_6mrr):
+    """SURVEY.md §8(f)-3 oracle pin: the :pme system = LJ + CoulombEwald real space (C oracle) + bonded + EwaldExclusion
+    over excluded-or-special pairs + PME reciprocal space with self/background terms (oracle/pme.py), against OpenMM's
+    forces_all_pme_exact / energy_all_pme_exact with the reference's own tolerances (test/protein.jl:267, :274)."""
+    from oracle import pme
+    g = golden_6mrr
+    sd = H.sixmrr_description(g)
+    alpha = pme.pme_alpha(1.0)
+    assert pme.pme_mesh_dims(g["box"], alpha) == (46, 46, 51)
+    inters = [o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=float(g["lj14scale"]), use_neighbors=True),
+              o.Inter(o.EWALD_REAL, o.CUT_DISTANCE, 1.0, weight_special=float(g["coulomb14scale"]), ewald_alpha=alpha,
+                      use_neighbors=True)]
+    orc = H.make_oracle(sd, inters, dtype=np.float64)
+    f, e, _ = orc.forces_allpairs(sd["coords"])
+    fb, eb = H.bonded_forces_oracle(g, sd["coords"])
+    fr, er, _ = pme.pme_reciprocal(sd["coords"], g["charge"], g["box"], r_cut=1.0, error_tol=0.0005, order=5)
+    fx, ex = pme.ewald_exclusion(sd["coords"], g["charge"], g["box"], np.concatenate([g["excluded"], g["special"]]))
+    e_tot = e + eb + er + ex + o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
+    assert np.linalg.norm(f + fb + fr + fx - g["forces_all_pme_exact"], axis=1).max() < 1e-7
+    assert abs(e_tot - float(g["energy_all_pme_exact"])) < 1e-5
