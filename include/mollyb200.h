@@ -138,6 +138,17 @@ int mb_set_specific(mb_ctx* ctx, int kind, int64_t n_terms, const int32_t* atom_
 /* forces(sys) / potential_energy(sys) of pairwise + specific interactions in one call (ADD semantics). */
 int mb_forces_energy_all(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, int64_t step_n);
 
+/* Particle-mesh Ewald, SURVEY.md §8(f)-3 — FIRST IMPLEMENTATION, not yet validated on a GPU (its parity test is
+ * marked xfail; the CPU checker oracle/pme.py is pinned against OpenMM's forces_all_pme_exact). Replaces the `PME`
+ * general interaction (src/interactions/ewald.jl:363-958; constructor PME(dist_cutoff, atoms, boundary; error_tol,
+ * order=5, eps_r)) and the `EwaldExclusion` specific interaction list (:979-1055) that src/setup.jl:1903-1912 builds
+ * from find_excluded_pairs(eligible, special): pairs = excluded OR special, 1-based. Use together with an
+ * MB_EWALD_REAL pairwise interaction of the same r_cut / error_tol (ewald_alpha = sqrt(-ln(2 error_tol)) / r_cut).
+ * Once set, mb_forces_energy_all and mb_simulate_vv add the reciprocal-space + exclusion forces (and energies incl.
+ * the self and neutralising-background terms) after the pair kernel. order = 0 switches it off; only order 5 exists. */
+int mb_set_pme(mb_ctx* ctx, double r_cut, double error_tol, int order, double eps_r, int64_t n_pairs,
+               const int32_t* pair_i, const int32_t* pair_j);
+
 /* simulate!(sys, VelocityVerlet(dt, coupling, remove_CM_motion), n_steps) hot loop
  * (src/simulators.jl:547-668): wrap, [CM removal when init_step==0], neighbours, F0, then n_steps of
  * kick / drift / wrap / forces / kick / CM removal (every remove_cm_every steps; 0 = never) /

@@ -206,6 +206,20 @@ TreeNeighborFinder = GPUNeighborFinder
 
 
 @dataclass
+class PME:
+    """PME(dist_cutoff, atoms, boundary; error_tol=0.0005, order=5, ϵr=1.0) general interaction
+    (src/interactions/ewald.jl:363-421) together with the EwaldExclusion list that src/setup.jl:1903-1912 builds from
+    find_excluded_pairs(eligible, special): `excluded_pairs` here = the excluded OR special pairs, 1-based (m,2).
+    Use with CoulombEwald(dist_cutoff, error_tol) as the pairwise interaction. First implementation: see
+    include/mollyb200.h (mb_set_pme) for its validation status."""
+    dist_cutoff: float
+    error_tol: float = 0.0005
+    order: int = 5
+    eps_r: float = 1.0
+    excluded_pairs: object = None
+
+
+@dataclass
 class InteractionList2Atoms:
     """InteractionList2Atoms of HarmonicBond (src/types.jl:89-157, interactions/harmonic_bond.jl): 1-based is/js,
     per-term k (kJ mol^-1 nm^-2) and r0 (nm)."""
@@ -281,7 +295,7 @@ class System:
     """
 
     def __init__(self, atoms, coords, boundary, velocities=None, pairwise_inters=(), neighbor_finder=None,
-                 dtype=np.float32, device: int = 0, k=BOLTZMANN_K, specific_inter_lists=()):
+                 dtype=np.float32, device: int = 0, k=BOLTZMANN_K, specific_inter_lists=(), general_inters=()):
         self.dtype = np.dtype(dtype)
         if isinstance(atoms, np.ndarray) and atoms.dtype.names:
             self.atoms = np.ascontiguousarray(atoms.astype(atom_dtype(self.dtype)))
@@ -294,6 +308,7 @@ class System:
         self.pairwise_inters = tuple(pairwise_inters)
         self.neighbor_finder = neighbor_finder
         self.specific_inter_lists = tuple(specific_inter_lists)
+        self.general_inters = tuple(general_inters)
         self.device = device
         self.k = k
         self._ctx = None
@@ -348,6 +363,15 @@ class System:
         for kind, (idx, par) in by_kind.items():
             idx, par = np.ascontiguousarray(idx), np.ascontiguousarray(par)
             capi.check(L.mb_set_specific(ctx, kind, len(idx), idx.ctypes.data, par.ctypes.data))
+
+        for gi in self.general_inters:
+            if not isinstance(gi, PME):
+                raise ValueError("only PME is supported as a general interaction")
+            pairs = np.zeros((0, 2), np.int32) if gi.excluded_pairs is None else np.asarray(gi.excluded_pairs, np.int32).reshape(-1, 2)
+            pi, pj = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+            self._keep_pme = (pi, pj)
+            capi.check(L.mb_set_pme(ctx, float(gi.dist_cutoff), float(gi.error_tol), int(gi.order), float(gi.eps_r), len(pi),
+                                    pi.ctypes.data, pj.ctypes.data))
 
     def close(self):
         if self._ctx is not None:
@@ -417,7 +441,7 @@ def forces_energy(sys: System, step_n: int = 0):
     ctx = sys.engine()
     fs = np.zeros((sys.n, 3), sys.dtype)
     pe = np.zeros(1, sys.dtype)
-    if sys.specific_inter_lists:
+    if sys.specific_inter_lists or sys.general_inters:
         capi.check(sys._L.mb_forces_energy_all(ctx, _ptr(sys.coords), fs.ctypes.data, pe.ctypes.data, step_n))
     else:
         capi.check(sys._L.mb_forces_energy(ctx, _ptr(sys.coords), fs.ctypes.data, pe.ctypes.data, None, step_n))

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "force.cuh"
 #include "pair.cuh"
+#include "pme.cuh"
 #include "vv.cuh"
 
 namespace mb {
@@ -164,6 +165,32 @@ struct Nccl {
     }
 };
 static Nccl g_nccl;
+
+// cuFFT, bound at run time like NCCL (only PME systems need it). Plain library FFT: the spreading, convolution and
+// interpolation kernels around it are ours (pme.cuh).
+struct Cufft {
+    void* lib = nullptr;
+    int (*Plan3d)(int*, int, int, int, int) = nullptr;
+    int (*SetStream)(int, cudaStream_t) = nullptr;
+    int (*ExecC2C)(int, void*, void*, int) = nullptr;
+    int (*ExecZ2Z)(int, void*, void*, int) = nullptr;
+    int (*Destroy)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        lib = dlopen("libcufft.so.11", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libcufft.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+#define MB_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) return false
+        MB_SYM(Plan3d, "cufftPlan3d");
+        MB_SYM(SetStream, "cufftSetStream");
+        MB_SYM(ExecC2C, "cufftExecC2C");
+        MB_SYM(ExecZ2Z, "cufftExecZ2Z");
+        MB_SYM(Destroy, "cufftDestroy");
+#undef MB_SYM
+        return true;
+    }
+};
+static Cufft g_cufft;
 #define MB_NCCL(call)                                                                                       \
     do {                                                                                                    \
         ncclResult_t r__ = (call);                                                                          \
@@ -235,6 +262,7 @@ class EngineBase {
     virtual int set_profiling(int enable) = 0;
     virtual int comm_init(const void* uid, int rank, int nranks) = 0;
     virtual int set_specific(int kind, int64_t n, const int32_t* idx, const double* par) = 0;
+    virtual int set_pme(double r_cut, double error_tol, int order, double eps_r, int64_t n_pairs, const int32_t* pi, const int32_t* pj) = 0;
 };
 
 template <typename T>
@@ -262,6 +290,7 @@ class Engine : public EngineBase {
     ~Engine() override {
         destroy_graph();
         p2p_close();
+        if (pme_plan_ >= 0 && g_cufft.Destroy) g_cufft.Destroy(pme_plan_);
         if (own_stream_) cudaStreamDestroy(stream_);
     }
 
@@ -677,11 +706,13 @@ class Engine : public EngineBase {
         destroy_graph();  // the step graph bakes the term counts in
         return MB_OK;
     }
-    bool has_specific() const { return sp_n_[0] + sp_n_[1] + sp_n_[2] > 0; }
+    bool has_lists() const { return sp_n_[0] + sp_n_[1] + sp_n_[2] > 0; }
+    bool has_specific() const { return has_lists() || pme_on_; }  // everything that is added after the pair kernel
     // add the bonded forces to f4 (slot order on the brick path, original order on the all-pairs path);
     // with energy: per-kernel partials are summed into d_sp_energy_ (double, device)
     int launch_bonded(bool energy) {
         if (!has_specific()) return MB_OK;
+        MB_CUDA(d_sp_partial_.ensure(64 * sizeof(double)));  // (set_specific sizes it for the lists; PME alone needs it to exist)
         const int* slot_of = (path_ == 1) ? d_inv_orig_.as<int>() : nullptr;
         BoxT bx;
         for (int d = 0; d < 3; d++) bx.L[d] = box_[d];
@@ -699,12 +730,149 @@ class Engine : public EngineBase {
             L.par[kind] = d_sp_par_k_[kind].p;
             total_blk += L.nblk[kind];
         }
-        if (energy) bonded_kernel<T, true><<<total_blk, BONDED_THREADS, 0, stream_>>>(L, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part);
-        else bonded_kernel<T, false><<<total_blk, BONDED_THREADS, 0, stream_>>>(L, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part);
-        launches_++;
-        if (energy) {
-            sum_partials_kernel<<<1, 256, 0, stream_>>>(total_blk, part, d_sp_energy_.as<double>());
+        if (total_blk > 0) {
+            if (energy) bonded_kernel<T, true><<<total_blk, BONDED_THREADS, 0, stream_>>>(L, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part);
+            else bonded_kernel<T, false><<<total_blk, BONDED_THREADS, 0, stream_>>>(L, slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, part);
             launches_++;
+            if (energy) {
+                sum_partials_kernel<<<1, 256, 0, stream_>>>(total_blk, part, d_sp_energy_.as<double>());
+                launches_++;
+            }
+        }
+        MB_CUDA(cudaGetLastError());
+        if (pme_on_) MB_TRY(launch_pme(energy));
+        return MB_OK;
+    }
+
+    // ---- PME reciprocal space + Ewald exclusions (pme.cuh) -------------------------------
+    int set_pme(double r_cut, double error_tol, int order, double eps_r, int64_t n_pairs, const int32_t* pi, const int32_t* pj) override {
+        if (order == 0) { pme_on_ = false; return MB_OK; }
+        if (order != PME_ORDER) return set_error(MB_ERR_INVALID, "mb_set_pme: only B-spline order 5 is implemented (the reference's default)");
+        if (!(r_cut > 0) || !(error_tol > 0 && error_tol < 0.5) || !(eps_r > 0) || n_pairs < 0 || (n_pairs > 0 && (!pi || !pj)))
+            return set_error(MB_ERR_INVALID, "mb_set_pme: bad arguments");
+        if (n_ <= 0) return set_error(MB_ERR_STATE, "mb_set_pme: set atoms first");
+        if (!g_cufft.load()) return set_error(MB_ERR_INVALID, "mb_set_pme: libcufft could not be loaded");
+        pme_pairs_.resize((size_t)2 * n_pairs);
+        for (int64_t k = 0; k < n_pairs; k++) {
+            const int a = pi[k] - 1, b = pj[k] - 1;  // 1-based in
+            if (a < 0 || b < 0 || a >= n_ || b >= n_) return set_error(MB_ERR_INVALID, "mb_set_pme: pair index out of bounds");
+            pme_pairs_[2 * k] = a;
+            pme_pairs_[2 * k + 1] = b;
+        }
+        pme_rc_ = r_cut; pme_tol_ = error_tol; pme_epsr_ = eps_r;
+        pme_on_ = true;
+        pme_ready_ = false;
+        destroy_graph();  // the captured step does not contain the PME launches
+        return MB_OK;
+    }
+    // grid dimensions, B-spline moduli, plan, self energy: ewald.jl:363-421 (constructor) and :947-956
+    int pme_prepare() {
+        bool same_box = pme_ready_;
+        for (int d = 0; d < 3; d++) same_box = same_box && (pme_g_.L[d] == box_[d]);
+        if (same_box) return MB_OK;
+        pme_alpha_ = std::sqrt(-std::log(2.0 * pme_tol_)) / pme_rc_;
+        for (int d = 0; d < 3; d++) {
+            pme_g_.L[d] = box_[d];
+            pme_g_.K[d] = std::max((int)std::ceil(2.0 * pme_alpha_ * box_[d] / (3.0 * std::pow(pme_tol_, 0.2))), 6);
+        }
+        // B-spline moduli (ewald.jl:311-361)
+        const int order = PME_ORDER;
+        std::vector<double> data(order, 0.0);
+        data[0] = 1.0;
+        for (int k = 3; k < order; k++) {
+            const double d = 1.0 / (k - 1.0);
+            data[k - 1] = 0.0;
+            for (int l = 1; l <= k - 2; l++) data[k - l - 1] = d * (l * data[k - l - 2] + (k - l) * data[k - l - 1]);
+            data[0] *= d;
+        }
+        {
+            const double d = 1.0 / (order - 1.0);
+            data[order - 1] = 0.0;
+            for (int l = 1; l <= order - 2; l++) data[order - l - 1] = d * (l * data[order - l - 2] + (order - l) * data[order - l - 1]);
+            data[0] *= d;
+        }
+        const double two_pi = 6.283185307179586476925;
+        for (int d = 0; d < 3; d++) {
+            const int nd = pme_g_.K[d];
+            std::vector<double> bs((size_t)std::max(nd, order + 1), 0.0), mod(nd);
+            for (int i = 0; i < order; i++) bs[i + 1] = data[i];
+            for (int i = 0; i < nd; i++) {
+                double sc = 0, ss = 0;
+                for (int j = 0; j < nd; j++) {
+                    const double arg = two_pi * i * j / nd;
+                    sc += bs[j] * std::cos(arg);
+                    ss += bs[j] * std::sin(arg);
+                }
+                mod[i] = sc * sc + ss * ss;
+            }
+            for (int i = 0; i < nd; i++)
+                if (mod[i] < 1e-7) mod[i] = 0.5 * (mod[(i - 1 + nd) % nd] + mod[(i + 1) % nd]);
+            MB_CUDA(d_pme_bsm_[d].ensure((size_t)nd * sizeof(double)));
+            MB_CUDA(cudaMemcpy(d_pme_bsm_[d].p, mod.data(), (size_t)nd * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        const size_t total = (size_t)pme_g_.K[0] * pme_g_.K[1] * pme_g_.K[2];
+        MB_CUDA(d_pme_grid_.ensure(total * sizeof(T2)));
+        const int conv_blk = (int)((total + PME_THREADS - 1) / PME_THREADS);
+        const int ex_blk = (int)((pme_pairs_.size() / 2 + BONDED_THREADS - 1) / BONDED_THREADS);
+        MB_CUDA(d_pme_partial_.ensure((size_t)(conv_blk + ex_blk + 8) * sizeof(double)));
+        if (!pme_pairs_.empty()) {
+            MB_CUDA(d_pme_pairs_.ensure(pme_pairs_.size() * sizeof(int)));
+            MB_CUDA(cudaMemcpy(d_pme_pairs_.p, pme_pairs_.data(), pme_pairs_.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        if (pme_plan_ >= 0) { g_cufft.Destroy(pme_plan_); pme_plan_ = -1; }
+        const int type = (sizeof(T) == 4) ? 0x29 /* CUFFT_C2C */ : 0x69 /* CUFFT_Z2Z */;
+        if (g_cufft.Plan3d(&pme_plan_, pme_g_.K[0], pme_g_.K[1], pme_g_.K[2], type) != 0) {
+            pme_plan_ = -1;
+            return set_error(MB_ERR_CUDA, "cufftPlan3d failed");
+        }
+        if (g_cufft.SetStream(pme_plan_, stream_) != 0) return set_error(MB_ERR_CUDA, "cufftSetStream failed");
+        // self and neutralising-background energy (ewald.jl:947-956)
+        double qs = 0, q2 = 0;
+        for (int64_t i = 0; i < n_; i++) { qs += (double)h_charge_[i]; q2 += (double)h_charge_[i] * (double)h_charge_[i]; }
+        const double f_div = pme_ke_ / pme_epsr_;
+        const double V = box_[0] * box_[1] * box_[2];
+        const double pi_ = 3.14159265358979323846;
+        pme_self_e_ = -f_div * q2 * pme_alpha_ / std::sqrt(pi_) - f_div * pi_ * qs * qs / (2.0 * V * pme_alpha_ * pme_alpha_);
+        pme_ready_ = true;
+        return MB_OK;
+    }
+    int launch_pme(bool energy) {
+        MB_TRY(pme_prepare());
+        const int nb = (int)((n_ + PME_THREADS - 1) / PME_THREADS);
+        const size_t total = (size_t)pme_g_.K[0] * pme_g_.K[1] * pme_g_.K[2];
+        const int conv_blk = (int)((total + PME_THREADS - 1) / PME_THREADS);
+        const int n_ex = (int)(pme_pairs_.size() / 2);
+        const int ex_blk = (n_ex + BONDED_THREADS - 1) / BONDED_THREADS;
+        const double f_div = pme_ke_ / pme_epsr_;
+        const double pi_ = 3.14159265358979323846;
+        const double factor = pi_ * pi_ / (pme_alpha_ * pme_alpha_);
+        const double boxfactor = pi_ * box_[0] * box_[1] * box_[2];
+        double* part = d_pme_partial_.as<double>();
+        T2* grid = d_pme_grid_.as<T2>();
+        MB_CUDA(cudaMemsetAsync(grid, 0, total * sizeof(T2), stream_));
+        pme_spread_kernel<T><<<nb, PME_THREADS, 0, stream_>>>((int)n_, pme_g_, d_pos4_.as<T4>(), grid);
+        auto fft = [&](int dir) -> int {
+            const int rc = (sizeof(T) == 4) ? g_cufft.ExecC2C(pme_plan_, grid, grid, dir) : g_cufft.ExecZ2Z(pme_plan_, grid, grid, dir);
+            return rc == 0 ? MB_OK : set_error(MB_ERR_CUDA, "cufftExec failed");
+        };
+        MB_TRY(fft(-1));
+        if (energy) pme_conv_kernel<T, true><<<conv_blk, PME_THREADS, 0, stream_>>>(pme_g_, f_div, factor, boxfactor, d_pme_bsm_[0].as<double>(), d_pme_bsm_[1].as<double>(), d_pme_bsm_[2].as<double>(), grid, part);
+        else pme_conv_kernel<T, false><<<conv_blk, PME_THREADS, 0, stream_>>>(pme_g_, f_div, factor, boxfactor, d_pme_bsm_[0].as<double>(), d_pme_bsm_[1].as<double>(), d_pme_bsm_[2].as<double>(), grid, part);
+        MB_TRY(fft(1));
+        pme_interp_kernel<T><<<nb, PME_THREADS, 0, stream_>>>((int)n_, pme_g_, d_pos4_.as<T4>(), grid, d_f4_.as<T4>());
+        launches_ += 3;
+        if (n_ex > 0) {
+            const int* slot_of = (path_ == 1) ? d_inv_orig_.as<int>() : nullptr;
+            BoxT bx;
+            for (int d = 0; d < 3; d++) bx.L[d] = box_[d];
+            if (energy) ewald_exclusion_kernel<T, true><<<ex_blk, BONDED_THREADS, 0, stream_>>>(n_ex, d_pme_pairs_.as<int>(), slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, pme_alpha_, f_div, part + conv_blk);
+            else ewald_exclusion_kernel<T, false><<<ex_blk, BONDED_THREADS, 0, stream_>>>(n_ex, d_pme_pairs_.as<int>(), slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, pme_alpha_, f_div, part + conv_blk);
+            launches_++;
+        }
+        if (energy) {
+            sum_partials_kernel<<<1, 256, 0, stream_>>>(conv_blk + (n_ex > 0 ? ex_blk : 0), part, d_sp_energy_.as<double>());
+            add_const_kernel<<<1, 1, 0, stream_>>>(d_sp_energy_.as<double>(), pme_self_e_);
+            launches_ += 2;
         }
         MB_CUDA(cudaGetLastError());
         return MB_OK;
@@ -1594,6 +1762,7 @@ class Engine : public EngineBase {
             cm_pending = true;
         }
         const bool dec = decomposed() && path_ == 1;
+        if (dec && pme_on_) return set_error(MB_ERR_INVALID, "PME is not available in decomposed (multi-GPU) runs yet");
         if (dec) {
             // lists built from here on cover only the owned slab
             build_b0_ = own_b0_;
@@ -1613,7 +1782,8 @@ class Engine : public EngineBase {
 
         // CUDA-graph path: static per-step sequence (remove_CM_motion in {0,1}, no stage timers requested)
         bool use_graph = graph_enabled_ && !graph_failed_ && !prof_.enabled && c.do_cm >= 0 && p->n_steps >= 4 &&
-                         !(cm_pending && c.do_cm == 0) && !dec;  // the decomposed step issues NCCL calls with per-rebuild sizes
+                         !(cm_pending && c.do_cm == 0) && !dec &&  // the decomposed step issues NCCL calls with per-rebuild sizes
+                         !pme_on_;                                  // cuFFT launches stay outside the captured step for now
         if (use_graph) {
             GraphKey key{path_, c.do_cm, c.thermostat ? 1 : 0, geom_version_, rebuild_every_, dual_ ? 1 : 0, p->dt, p->andersen_kT, p->andersen_prob, n_};
             if (!graph_exec_ || !(key == graph_key_)) {
@@ -1795,6 +1965,13 @@ class Engine : public EngineBase {
     int plan_key_[3] = {-1, -1, -1};
     int64_t sp_n_[3] = {0, 0, 0};
     DevBuf d_sp_idx_k_[3], d_sp_par_k_[3], d_sp_partial_, d_sp_energy_;
+    // PME (pme.cuh)
+    bool pme_on_ = false, pme_ready_ = false;
+    double pme_rc_ = 0, pme_tol_ = 0, pme_epsr_ = 1, pme_alpha_ = 0, pme_self_e_ = 0, pme_ke_ = 138.93545764;
+    PmeGeom pme_g_ = {{0, 0, 0}, {0, 0, 0}};
+    int pme_plan_ = -1;
+    std::vector<int> pme_pairs_;
+    DevBuf d_pme_grid_, d_pme_bsm_[3], d_pme_partial_, d_pme_pairs_;
     DevBuf d_mass_in_, d_charge_in_, d_ljp_in_;
     DevBuf d_pos4_, d_vel4_, d_f4_, d_xref4_, d_lj2_, d_orig_, d_inv_orig_, d_mass_;
     DevBuf d_pos4_t_, d_vel4_t_, d_lj2_t_, d_orig_t_, d_mass_t_;
@@ -1899,6 +2076,10 @@ int mb_forces_energy_all(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe
 int mb_set_specific(mb_ctx* ctx, int kind, int64_t n_terms, const int32_t* atom_idx, const double* params) {
     MB_CTX_GUARD(ctx);
     return ctx->e->set_specific(kind, n_terms, atom_idx, params);
+}
+int mb_set_pme(mb_ctx* ctx, double r_cut, double error_tol, int order, double eps_r, int64_t n_pairs, const int32_t* pi, const int32_t* pj) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->set_pme(r_cut, error_tol, order, eps_r, n_pairs, pi, pj);
 }
 int mb_simulate_vv(mb_ctx* ctx, void* coords, void* vels, const mb_vv_params_t* p) { MB_CTX_GUARD(ctx); return ctx->e->simulate_vv(coords, vels, p); }
 int mb_remove_cm_motion(mb_ctx* ctx, void* vels) { MB_CTX_GUARD(ctx); return ctx->e->remove_cm(vels); }
