@@ -148,6 +148,11 @@ int mb_forces_energy_all(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe
  * the self and neutralising-background terms) after the pair kernel. order = 0 switches it off; only order 5 exists. */
 int mb_set_pme(mb_ctx* ctx, double r_cut, double error_tol, int order, double eps_r, int64_t n_pairs,
                const int32_t* pair_i, const int32_t* pair_j);
+/* The host-side PME plan (no GPU needed; what the PME constructor computes, ewald.jl:373, :484-487, :311-361): Ewald
+ * alpha, mesh dimensions, and (if moduli_out != NULL, capacity >= K0 + K1 + K2) the B-spline moduli of the three
+ * dimensions back to back. */
+int mb_pme_plan(const double box[3], double r_cut, double error_tol, int order, double* alpha_out, int32_t mesh_out[3],
+                double* moduli_out, int capacity);
 
 /* simulate!(sys, VelocityVerlet(dt, coupling, remove_CM_motion), n_steps) hot loop
  * (src/simulators.jl:547-668): wrap, [CM removal when init_step==0], neighbours, F0, then n_steps of

@@ -17,7 +17,7 @@ EXPORTED = [
     "mb_set_box", "mb_set_inters", "mb_set_exceptions", "mb_set_neighbor_policy", "mb_forces", "mb_energy",
     "mb_forces_energy", "mb_simulate_vv", "mb_remove_cm_motion", "mb_kinetic_energy", "mb_rebuild_neighbors",
     "mb_stats", "mb_synchronize", "mb_set_capacity_scale", "mb_set_launch_config", "mb_comm_unique_id",
-    "mb_comm_init", "mb_decomp_plan", "mb_set_profiling", "mb_set_specific", "mb_forces_energy_all", "mb_set_pme",
+    "mb_comm_init", "mb_decomp_plan", "mb_set_profiling", "mb_set_specific", "mb_forces_energy_all", "mb_set_pme", "mb_pme_plan",
 ]
 
 
@@ -96,6 +96,7 @@ def load():
     L.mb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.mb_set_specific.argtypes = [vp, C.c_int, i64, vp, vp]
     L.mb_set_pme.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_double, i64, vp, vp]
+    L.mb_pme_plan.argtypes = [vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, C.c_int]
     L.mb_forces_energy_all.argtypes = [vp, vp, vp, vp, i64]
     L.mb_decomp_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(i32), vp, C.POINTER(i32), C.c_int]
     L.mb_set_profiling.argtypes = [vp, C.c_int]

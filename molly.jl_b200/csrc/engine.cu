@@ -240,6 +240,51 @@ static void decomp_plan(int ncz, int h, int nranks, int rank, const int* layer_s
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PME plan (pure host logic, exported as mb_pme_plan so it is tested on the CPU against oracle/pme.py):
+// alpha = sqrt(-ln(2 tol)) / rc (ewald.jl:373), mesh dims = max(6, ceil(2 alpha L / (3 tol^0.2))) (:484-487),
+// B-spline moduli (:311-361).
+// ---------------------------------------------------------------------------------------------
+static void pme_plan_host(const double box[3], double r_cut, double error_tol, int order, double* alpha_out, int K[3],
+                          std::vector<double> moduli[3]) {
+    const double alpha = std::sqrt(-std::log(2.0 * error_tol)) / r_cut;
+    *alpha_out = alpha;
+    for (int d = 0; d < 3; d++) K[d] = std::max((int)std::ceil(2.0 * alpha * box[d] / (3.0 * std::pow(error_tol, 0.2))), 6);
+    std::vector<double> data(order, 0.0);
+    data[0] = 1.0;
+    for (int k = 3; k < order; k++) {
+        const double d = 1.0 / (k - 1.0);
+        data[k - 1] = 0.0;
+        for (int l = 1; l <= k - 2; l++) data[k - l - 1] = d * (l * data[k - l - 2] + (k - l) * data[k - l - 1]);
+        data[0] *= d;
+    }
+    {
+        const double d = 1.0 / (order - 1.0);
+        data[order - 1] = 0.0;
+        for (int l = 1; l <= order - 2; l++) data[order - l - 1] = d * (l * data[order - l - 2] + (order - l) * data[order - l - 1]);
+        data[0] *= d;
+    }
+    const double two_pi = 6.283185307179586476925;
+    for (int d = 0; d < 3; d++) {
+        const int nd = K[d];
+        std::vector<double> bs((size_t)std::max(nd, order + 1), 0.0);
+        std::vector<double>& mod = moduli[d];
+        mod.assign(nd, 0.0);
+        for (int i = 0; i < order; i++) bs[i + 1] = data[i];
+        for (int i = 0; i < nd; i++) {
+            double sc = 0, ss = 0;
+            for (int j = 0; j < nd; j++) {
+                const double arg = two_pi * i * j / nd;
+                sc += bs[j] * std::cos(arg);
+                ss += bs[j] * std::sin(arg);
+            }
+            mod[i] = sc * sc + ss * ss;
+        }
+        for (int i = 0; i < nd; i++)
+            if (mod[i] < 1e-7) mod[i] = 0.5 * (mod[(i - 1 + nd) % nd] + mod[(i + 1) % nd]);
+    }
+}
+
 class EngineBase {
    public:
     virtual ~EngineBase() {}
@@ -770,45 +815,12 @@ class Engine : public EngineBase {
         bool same_box = pme_ready_;
         for (int d = 0; d < 3; d++) same_box = same_box && (pme_g_.L[d] == box_[d]);
         if (same_box) return MB_OK;
-        pme_alpha_ = std::sqrt(-std::log(2.0 * pme_tol_)) / pme_rc_;
+        std::vector<double> moduli[3];
+        pme_plan_host(box_, pme_rc_, pme_tol_, PME_ORDER, &pme_alpha_, pme_g_.K, moduli);
         for (int d = 0; d < 3; d++) {
             pme_g_.L[d] = box_[d];
-            pme_g_.K[d] = std::max((int)std::ceil(2.0 * pme_alpha_ * box_[d] / (3.0 * std::pow(pme_tol_, 0.2))), 6);
-        }
-        // B-spline moduli (ewald.jl:311-361)
-        const int order = PME_ORDER;
-        std::vector<double> data(order, 0.0);
-        data[0] = 1.0;
-        for (int k = 3; k < order; k++) {
-            const double d = 1.0 / (k - 1.0);
-            data[k - 1] = 0.0;
-            for (int l = 1; l <= k - 2; l++) data[k - l - 1] = d * (l * data[k - l - 2] + (k - l) * data[k - l - 1]);
-            data[0] *= d;
-        }
-        {
-            const double d = 1.0 / (order - 1.0);
-            data[order - 1] = 0.0;
-            for (int l = 1; l <= order - 2; l++) data[order - l - 1] = d * (l * data[order - l - 2] + (order - l) * data[order - l - 1]);
-            data[0] *= d;
-        }
-        const double two_pi = 6.283185307179586476925;
-        for (int d = 0; d < 3; d++) {
-            const int nd = pme_g_.K[d];
-            std::vector<double> bs((size_t)std::max(nd, order + 1), 0.0), mod(nd);
-            for (int i = 0; i < order; i++) bs[i + 1] = data[i];
-            for (int i = 0; i < nd; i++) {
-                double sc = 0, ss = 0;
-                for (int j = 0; j < nd; j++) {
-                    const double arg = two_pi * i * j / nd;
-                    sc += bs[j] * std::cos(arg);
-                    ss += bs[j] * std::sin(arg);
-                }
-                mod[i] = sc * sc + ss * ss;
-            }
-            for (int i = 0; i < nd; i++)
-                if (mod[i] < 1e-7) mod[i] = 0.5 * (mod[(i - 1 + nd) % nd] + mod[(i + 1) % nd]);
-            MB_CUDA(d_pme_bsm_[d].ensure((size_t)nd * sizeof(double)));
-            MB_CUDA(cudaMemcpy(d_pme_bsm_[d].p, mod.data(), (size_t)nd * sizeof(double), cudaMemcpyHostToDevice));
+            MB_CUDA(d_pme_bsm_[d].ensure(moduli[d].size() * sizeof(double)));
+            MB_CUDA(cudaMemcpy(d_pme_bsm_[d].p, moduli[d].data(), moduli[d].size() * sizeof(double), cudaMemcpyHostToDevice));
         }
         const size_t total = (size_t)pme_g_.K[0] * pme_g_.K[1] * pme_g_.K[2];
         MB_CUDA(d_pme_grid_.ensure(total * sizeof(T2)));
@@ -2116,6 +2128,22 @@ int mb_decomp_plan(int ncz, int halo_layers, int nranks, int rank, const int32_t
     for (size_t k = 0; k < rcv.size(); k++) { recv_out[3 * k] = rcv[k].peer; recv_out[3 * k + 1] = rcv[k].start; recv_out[3 * k + 2] = rcv[k].count; }
     *n_send = (int32_t)snd.size();
     *n_recv = (int32_t)rcv.size();
+    return MB_OK;
+}
+int mb_pme_plan(const double box[3], double r_cut, double error_tol, int order, double* alpha_out, int32_t mesh_out[3],
+                double* moduli_out, int capacity) {
+    if (!box || !alpha_out || !mesh_out || !(r_cut > 0) || !(error_tol > 0 && error_tol < 0.5) || order < 3 || order > 8)
+        return mb::set_error(MB_ERR_INVALID, "mb_pme_plan: bad arguments");
+    std::vector<double> moduli[3];
+    int K[3];
+    mb::pme_plan_host(box, r_cut, error_tol, order, alpha_out, K, moduli);
+    for (int d = 0; d < 3; d++) mesh_out[d] = K[d];
+    if (moduli_out) {
+        if (K[0] + K[1] + K[2] > capacity) return mb::set_error(MB_ERR_CAPACITY, "mb_pme_plan: capacity");
+        size_t o = 0;
+        for (int d = 0; d < 3; d++)
+            for (double v : moduli[d]) moduli_out[o++] = v;
+    }
     return MB_OK;
 }
 int mb_comm_init(mb_ctx* ctx, const void* unique_id128, int rank, int nranks) {

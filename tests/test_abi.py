@@ -68,3 +68,26 @@ def test_interaction_descriptors():
     from molly_jl_b200.api import _pairs_from
     assert _pairs_from(nf.eligible, 3, want_true=False).tolist() == [[1, 2]]
     assert _pairs_from(nf.special, 3, want_true=True).tolist() == [[1, 3]]
+
+
+def test_pme_plan_matches_oracle():
+    """Host half of the PME row: alpha, mesh dimensions and B-spline moduli computed by the library
+    (mb_pme_plan, no GPU) against the numpy restatement that is pinned on OpenMM's goldens (oracle/pme.py)."""
+    import ctypes as C
+    import numpy as np
+    from oracle import pme
+    L = mb.capi.load()
+    for box, rc, tol in (((5.676, 5.6627, 6.2963), 1.0, 0.0005), ((3.0, 4.1, 2.2), 0.9, 1e-4), ((1.0, 1.0, 1.0), 0.45, 0.01)):
+        b = (C.c_double * 3)(*box)
+        alpha = C.c_double()
+        mesh = (C.c_int32 * 3)()
+        mod = np.zeros(4096)
+        assert L.mb_pme_plan(b, rc, tol, 5, C.byref(alpha), mesh, mod.ctypes.data, len(mod)) == 0
+        a_ref = pme.pme_alpha(rc, tol)
+        k_ref = pme.pme_mesh_dims(box, a_ref, tol)
+        assert abs(alpha.value - a_ref) < 1e-15 * a_ref * 4 and tuple(mesh) == k_ref
+        m_ref = np.concatenate(pme.bspline_moduli(5, k_ref))
+        assert np.allclose(mod[:len(m_ref)], m_ref, rtol=1e-12, atol=1e-15)
+    alpha = C.c_double()
+    mesh = (C.c_int32 * 3)()
+    assert L.mb_pme_plan(None, 1.0, 0.0005, 5, C.byref(alpha), mesh, None, 0) != 0  # bad arguments -> status, no crash
