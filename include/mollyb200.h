@@ -138,8 +138,9 @@ int mb_set_specific(mb_ctx* ctx, int kind, int64_t n_terms, const int32_t* atom_
 /* forces(sys) / potential_energy(sys) of pairwise + specific interactions in one call (ADD semantics). */
 int mb_forces_energy_all(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, int64_t step_n);
 
-/* Particle-mesh Ewald, SURVEY.md §8(f)-3 — FIRST IMPLEMENTATION, not yet validated on a GPU (its parity test is
- * marked xfail; the CPU checker oracle/pme.py is pinned against OpenMM's forces_all_pme_exact). Replaces the `PME`
+/* Particle-mesh Ewald, SURVEY.md §8(f)-3 — FIRST IMPLEMENTATION, not yet run on a GPU (its GPU parity test is marked
+ * xfail). The arithmetic of its kernels is validated on the host (tests/test_pme_host.py: the __host__ __device__
+ * per-item functions reproduce OpenMM's forces_all_pme_exact to < 1e-7 kJ/mol/nm), the plan by mb_pme_plan's test. Replaces the `PME`
  * general interaction (src/interactions/ewald.jl:363-958; constructor PME(dist_cutoff, atoms, boundary; error_tol,
  * order=5, eps_r)) and the `EwaldExclusion` specific interaction list (:979-1055) that src/setup.jl:1903-1912 builds
  * from find_excluded_pairs(eligible, special): pairs = excluded OR special, 1-based. Use together with an

@@ -825,7 +825,7 @@ class Engine : public EngineBase {
         const size_t total = (size_t)pme_g_.K[0] * pme_g_.K[1] * pme_g_.K[2];
         MB_CUDA(d_pme_grid_.ensure(total * sizeof(T2)));
         const int conv_blk = (int)((total + PME_THREADS - 1) / PME_THREADS);
-        const int ex_blk = (int)((pme_pairs_.size() / 2 + BONDED_THREADS - 1) / BONDED_THREADS);
+        const int ex_blk = (int)((pme_pairs_.size() / 2 + PME_THREADS - 1) / PME_THREADS);
         MB_CUDA(d_pme_partial_.ensure((size_t)(conv_blk + ex_blk + 8) * sizeof(double)));
         if (!pme_pairs_.empty()) {
             MB_CUDA(d_pme_pairs_.ensure(pme_pairs_.size() * sizeof(int)));
@@ -854,7 +854,7 @@ class Engine : public EngineBase {
         const size_t total = (size_t)pme_g_.K[0] * pme_g_.K[1] * pme_g_.K[2];
         const int conv_blk = (int)((total + PME_THREADS - 1) / PME_THREADS);
         const int n_ex = (int)(pme_pairs_.size() / 2);
-        const int ex_blk = (n_ex + BONDED_THREADS - 1) / BONDED_THREADS;
+        const int ex_blk = (n_ex + PME_THREADS - 1) / PME_THREADS;
         const double f_div = pme_ke_ / pme_epsr_;
         const double pi_ = 3.14159265358979323846;
         const double factor = pi_ * pi_ / (pme_alpha_ * pme_alpha_);
@@ -875,10 +875,8 @@ class Engine : public EngineBase {
         launches_ += 3;
         if (n_ex > 0) {
             const int* slot_of = (path_ == 1) ? d_inv_orig_.as<int>() : nullptr;
-            BoxT bx;
-            for (int d = 0; d < 3; d++) bx.L[d] = box_[d];
-            if (energy) ewald_exclusion_kernel<T, true><<<ex_blk, BONDED_THREADS, 0, stream_>>>(n_ex, d_pme_pairs_.as<int>(), slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, pme_alpha_, f_div, part + conv_blk);
-            else ewald_exclusion_kernel<T, false><<<ex_blk, BONDED_THREADS, 0, stream_>>>(n_ex, d_pme_pairs_.as<int>(), slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), bx, pme_alpha_, f_div, part + conv_blk);
+            if (energy) ewald_exclusion_kernel<T, true><<<ex_blk, PME_THREADS, 0, stream_>>>(n_ex, d_pme_pairs_.as<int>(), slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), pme_g_, pme_alpha_, f_div, part + conv_blk);
+            else ewald_exclusion_kernel<T, false><<<ex_blk, PME_THREADS, 0, stream_>>>(n_ex, d_pme_pairs_.as<int>(), slot_of, d_pos4_.as<T4>(), d_f4_.as<T4>(), pme_g_, pme_alpha_, f_div, part + conv_blk);
             launches_++;
         }
         if (energy) {
