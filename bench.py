@@ -150,6 +150,11 @@ def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32):
     """Molly-algorithm CPU restatement (oracle): list every 10 steps with rc + 0.2 nm, all host threads."""
     from oracle import oracle as o
     if "golden" in sd:  # 6mrr: pairwise in C (threaded), bonded terms in numpy, f64
+        try:
+            import psutil
+            o.DEFAULT_THREADS = max(o.max_threads(), psutil.cpu_count(logical=False) or 1)  # not OMP_NUM_THREADS=1 of a launcher
+        except Exception:
+            pass
         t0 = time.perf_counter()
         H.oracle_vv_with_bonded(sd["golden"], sd["coords"].astype(np.float64), sd["velocities"].astype(np.float64), dt, steps,
                                 r_list=rc + 0.2, nl_every=10)

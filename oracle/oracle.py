@@ -104,8 +104,11 @@ def lib():
     return _lib
 
 
+DEFAULT_THREADS = 0  # 0 = whatever OpenMP reports; bench.py sets it (launchers like torchrun export OMP_NUM_THREADS=1)
+
+
 def max_threads() -> int:
-    return int(lib().orc_max_threads())
+    return int(DEFAULT_THREADS) if DEFAULT_THREADS else int(lib().orc_max_threads())
 
 
 @dataclass
