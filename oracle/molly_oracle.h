@@ -12,7 +12,8 @@ extern "C" {
 #endif
 
 enum { ORC_LJ = 0, ORC_COULOMB = 1, ORC_CRF = 2, ORC_EWALD_REAL = 3 };
-enum { ORC_CUT_NONE = 0, ORC_CUT_DISTANCE = 1, ORC_CUT_SHIFTED_POTENTIAL = 2, ORC_CUT_SHIFTED_FORCE = 3 };
+enum { ORC_CUT_NONE = 0, ORC_CUT_DISTANCE = 1, ORC_CUT_SHIFTED_POTENTIAL = 2, ORC_CUT_SHIFTED_FORCE = 3,
+       ORC_CUT_CUBIC_SPLINE = 4, ORC_CUT_POLYNOMIAL = 5 /* oracle only so far */ };
 enum { ORC_MIX_LORENTZ = 0, ORC_MIX_GEOMETRIC = 1 };
 
 /* Same field order as mb_inter_t in include/mollyb200.h so one ctypes struct serves both. */

@@ -72,7 +72,7 @@ typedef struct {
  * CRF:      src/interactions/coulomb.jl:748-814
  * Ewald-real: src/interactions/coulomb.jl:1395-1441 (exact erfc)
  * cutoffs:  src/cutoffs.jl:15-45 (NoCutoff / DistanceCutoff),
- *           :99-141 (ShiftedPotential), :143-190 (ShiftedForce)
+ *           :99-141 (ShiftedPotential), :143-190 (ShiftedForce), :192-253 (CubicSpline, Polynomial; LJ only)
  */
 static inline void FN(pair_eval)(const orc_inter_t *in, const FN(pairparm) * p, REAL r2, int special,
                                  REAL *fr_out, REAL *pe_out) {
@@ -117,6 +117,28 @@ static inline void FN(pair_eval)(const orc_inter_t *in, const FN(pairparm) * p, 
             f = f - fc;
             e = e + (r - rc) * fc - ec;
             if (!(r <= rc)) { f = 0; e = 0; }
+        } else if (in->cutoff_kind == ORC_CUT_CUBIC_SPLINE || in->cutoff_kind == ORC_CUT_POLYNOMIAL) {
+            /* two-point cutoffs, cutoffs.jl:23-29, :39-45: unchanged up to r_act, switched on (r_act, rc], zero beyond */
+            REAL ra = (REAL)in->r_act;
+            if (!(r <= ra)) {
+                REAL t = (r - ra) / (rc - ra);
+                if (in->cutoff_kind == ORC_CUT_CUBIC_SPLINE) { /* cutoffs.jl:192-215 */
+                    REAL sa = s2 / (ra * ra);
+                    sa = sa * sa * sa;
+                    REAL pe_act = 4 * eps * (sa * sa - sa);
+                    REAL dpe_act = -((24 * eps / ra) * (2 * sa * sa - sa));
+                    e = (2 * t * t * t - 3 * t * t + 1) * pe_act + (t * t * t - 2 * t * t + t) * (rc - ra) * dpe_act;
+                    f = -(6 * t * t - 6 * t) * pe_act / (rc - ra) - (3 * t * t - 4 * t + 1) * dpe_act;
+                } else { /* PolynomialCutoff, cutoffs.jl:241-253 */
+                    REAL t2 = t * t, t3 = t2 * t;
+                    REAL S = 1 - 6 * t3 * t2 + 15 * t2 * t2 - 10 * t3;
+                    REAL dS = (-30 * t2 * t2 + 60 * t3 - 30 * t2) / (rc - ra);
+                    REAL f0 = f, e0 = e;
+                    e = S * e0;
+                    f = S * f0 - dS * e0;
+                }
+                if (!(r <= rc)) { f = 0; e = 0; }
+            }
         }
         fr = (f / r) * w;
         pe = e * w;

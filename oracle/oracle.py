@@ -17,6 +17,7 @@ _LIB_PATH = os.path.join(_HERE, "libmollyoracle.so")
 
 LJ, COULOMB, CRF, EWALD_REAL = 0, 1, 2, 3
 CUT_NONE, CUT_DISTANCE, CUT_SHIFTED_POTENTIAL, CUT_SHIFTED_FORCE = 0, 1, 2, 3
+CUT_CUBIC_SPLINE, CUT_POLYNOMIAL = 4, 5  # two-point cutoffs (r_act, r_cut); oracle only so far
 MIX_LORENTZ, MIX_GEOMETRIC = 0, 1
 COULOMB_CONST = 138.93545764  # src/interactions/coulomb.jl:16
 BOLTZMANN_K = 8.31446261815324e-3  # src/units.jl:186-198 (kJ mol^-1 K^-1)
@@ -118,6 +119,7 @@ class Inter:
     kind: int
     cutoff_kind: int = CUT_NONE
     r_cut: float = 0.0
+    r_act: float = 0.0  # dist_activation of the two-point cutoffs
     weight_special: float = 1.0
     coulomb_const: float = COULOMB_CONST
     solvent_dielectric: float = 78.3  # coulomb.jl:676
@@ -127,7 +129,7 @@ class Inter:
     use_neighbors: bool = False
 
     def to_c(self) -> InterC:
-        return InterC(self.kind, self.cutoff_kind, self.r_cut, 0.0, self.weight_special, self.coulomb_const,
+        return InterC(self.kind, self.cutoff_kind, self.r_cut, self.r_act, self.weight_special, self.coulomb_const,
                       self.solvent_dielectric, self.ewald_alpha, self.sigma_mix, self.eps_mix, 0,
                       int(self.use_neighbors))
 

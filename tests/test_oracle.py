@@ -203,3 +203,22 @@ def test_6mrr_all_pme_openmm_golden(golden_6mrr):
     e_tot = e + eb + er + ex + o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
     assert np.linalg.norm(f + fb + fr + fx - g["forces_all_pme_exact"], axis=1).max() < 1e-7
     assert abs(e_tot - float(g["energy_all_pme_exact"])) < 1e-5
+
+
+def test_cutoff_literals_all_six():
+    """test/interactions.jl:1574-1635: LJ (sigma 0.3, eps 0.2) at r = 0.7 nm under the six cutoffs (dist_cut 0.8,
+    dist_act 0.6), and exactly zero at r = 1.0 / 0.95 nm. CubicSpline / Polynomial exist in the
+    oracle only so far."""
+    lit = [(o.CUT_NONE, -0.04196301990, -0.00492640193), (o.CUT_DISTANCE, -0.04196301990, -0.00492640193),
+           (o.CUT_SHIFTED_POTENTIAL, -0.04196301990, -0.00270785727), (o.CUT_SHIFTED_FORCE, -0.02537033587, -0.00104858887),
+           (o.CUT_CUBIC_SPLINE, -0.06201171875, -0.00312500000), (o.CUT_POLYNOMIAL, -0.06716652806, -0.00246320097)]
+    for kind, f_ref, e_ref in lit:
+        s = o.OracleSystem(box=np.array([2.0, 2.0, 2.0]), mass=np.ones(2), charge=np.ones(2), sigma=np.full(2, 0.3),
+                           eps=np.full(2, 0.2), inters=[o.Inter(o.LJ, kind, 0.8, r_act=0.6)])
+        f, e, _ = s.forces_allpairs(np.array([[1.0, 1.0, 1.0], [1.7, 1.0, 1.0]]))
+        # the reference's force(inter, dr, ...) is f with fs[i] -= f, fs[j] += f (src/force.jl:869-874)
+        assert abs(f[1, 0] - f_ref) < 1e-9 and abs(f[0, 0] + f_ref) < 1e-9 and abs(e - e_ref) < 1e-9
+        if kind != o.CUT_NONE:
+            for xj in (2.0, 1.95):  # minimum image: r = 1.0 and 0.95 nm, both beyond the cutoff
+                f, e, _ = s.forces_allpairs(np.array([[1.0, 1.0, 1.0], [xj, 1.0, 1.0]]))
+                assert np.abs(f).max() < 1e-12 and abs(e) < 1e-12
