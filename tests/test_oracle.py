@@ -222,3 +222,23 @@ def test_cutoff_literals_all_six():
             for xj in (2.0, 1.95):  # minimum image: r = 1.0 and 0.95 nm, both beyond the cutoff
                 f, e, _ = s.forces_allpairs(np.array([[1.0, 1.0, 1.0], [xj, 1.0, 1.0]]))
                 assert np.abs(f).max() < 1e-12 and abs(e) < 1e-12
+
+
+def test_water3_pme_openmm_literals():
+    """Second PME pin, on a non-cubic orthorhombic box (2.0 x 2.1 x 2.2 nm): three TIP3P waters, electrostatics only,
+    dist_cutoff 0.9 nm — the OpenMM energy / forces the reference's "Ewald" testset holds as literals
+    (test/interactions.jl:1683-1697; its tolerances: 2e-4 kJ/mol, 5e-4 kJ/mol/nm)."""
+    import os
+    from oracle import pme
+    w = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "water3.npz")))
+    rc = float(w["r_cut"])
+    alpha = pme.pme_alpha(rc)
+    assert pme.pme_mesh_dims(w["box"], alpha) == (18, 19, 20)
+    s = o.OracleSystem(box=w["box"], mass=w["mass"], charge=w["charge"], sigma=w["sigma"], eps=w["eps"],
+                       inters=[o.Inter(o.EWALD_REAL, o.CUT_DISTANCE, rc, ewald_alpha=alpha, use_neighbors=True)],
+                       excluded_pairs=w["excluded"], special_pairs=w["special"])
+    f, e, _ = s.forces_allpairs(w["coords"])
+    fr, er, _ = pme.pme_reciprocal(w["coords"], w["charge"], w["box"], r_cut=rc)
+    fx, ex = pme.ewald_exclusion(w["coords"], w["charge"], w["box"], w["excluded"], r_cut=rc)
+    assert np.linalg.norm(f + fr + fx - w["forces_pme"], axis=1).max() < 1e-7  # reference: 5e-4
+    assert abs(e + er + ex - float(w["energy_pme"])) < 1e-8                   # reference: 2e-4

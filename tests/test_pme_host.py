@@ -79,3 +79,36 @@ def test_pme_device_functions_on_host_vs_openmm(hostlib, golden_6mrr):
     assert np.linalg.norm(total - g["forces_all_pme_exact"], axis=1).max() < 1e-7
     e_tot = e + eb + e_recip + info["e_self"] + e_ex + o.lj_dispersion_correction_energy(g["sigma"], g["eps"], box, 1.0)
     assert abs(e_tot - float(g["energy_all_pme_exact"])) < 1e-5
+
+
+def test_pme_device_functions_on_host_water3(hostlib):
+    """Same chain on the reference's small PME case (orthorhombic 2.0 x 2.1 x 2.2 nm box, mesh 18 x 19 x 20): against
+    the OpenMM literals of test/interactions.jl:1683-1697."""
+    w = dict(np.load(os.path.join(ROOT, "tests", "golden", "water3.npz")))
+    n = len(w["coords"])
+    box = np.ascontiguousarray(w["box"], np.float64)
+    rc = float(w["r_cut"])
+    alpha = pme.pme_alpha(rc)
+    K = np.array(pme.pme_mesh_dims(box, alpha), np.int32)
+    bsm = [np.ascontiguousarray(m) for m in pme.bspline_moduli(5, tuple(K))]
+    pos4 = np.ascontiguousarray(np.concatenate([w["coords"], w["charge"][:, None]], 1), np.float64)
+    f_div = pme.COULOMB_CONST
+    grid = np.zeros((K[0], K[1], K[2], 2), np.float64)
+    hostlib.pmeh_spread(n, _ptr(K), _ptr(box), _ptr(pos4), _ptr(grid))
+    S = np.fft.fftn(grid[..., 0])
+    cg = np.ascontiguousarray(np.stack([S.real, S.imag], -1))
+    e_recip = hostlib.pmeh_conv(_ptr(K), _ptr(box), C.c_double(f_div), C.c_double(alpha), _ptr(bsm[0]), _ptr(bsm[1]), _ptr(bsm[2]), _ptr(cg))
+    pot = np.fft.ifftn(cg[..., 0] + 1j * cg[..., 1]) * K.prod()
+    pg = np.ascontiguousarray(np.stack([pot.real, pot.imag], -1))
+    f4 = np.zeros((n, 4), np.float64)
+    hostlib.pmeh_interp(n, _ptr(K), _ptr(box), _ptr(pos4), _ptr(pg), _ptr(f4))
+    pairs = np.ascontiguousarray(w["excluded"], np.int32)
+    e_ex = hostlib.pmeh_exclusion(len(pairs), _ptr(pairs), _ptr(box), _ptr(pos4), _ptr(f4), C.c_double(alpha), C.c_double(f_div))
+    s = o.OracleSystem(box=box, mass=w["mass"], charge=w["charge"], sigma=w["sigma"], eps=w["eps"],
+                       inters=[o.Inter(o.EWALD_REAL, o.CUT_DISTANCE, rc, ewald_alpha=alpha, use_neighbors=True)],
+                       excluded_pairs=w["excluded"], special_pairs=w["special"])
+    f, e, _ = s.forces_allpairs(w["coords"])
+    q = w["charge"]
+    e_self = -f_div * (q ** 2).sum() * alpha / np.sqrt(np.pi) - f_div * np.pi * q.sum() ** 2 / (2 * box.prod() * alpha ** 2)
+    assert np.linalg.norm(f + f4[:, :3] - w["forces_pme"], axis=1).max() < 1e-7
+    assert abs(e + e_recip + e_self + e_ex - float(w["energy_pme"])) < 1e-8

@@ -34,12 +34,25 @@ e += o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
 err = np.linalg.norm(f - g["forces_all_pme_exact"], axis=1).max()
 print("max|dF| =", err, "dE =", e - float(g["energy_all_pme_exact"]))
 assert err < 1e-6 and abs(e - float(g["energy_all_pme_exact"])) < 1e-3   # reference: 1e-7 / 1e-5 on the CPU in f64
+# the reference's small PME case (test/interactions.jl:1683-1697): 3 waters, orthorhombic box, all-pairs path
+w = dict(np.load(%(water)r))
+for dt_, tol_f, tol_e in ((np.float64, 1e-6, 1e-6), (np.float32, 5e-4, 2e-4)):   # f32: the reference's own tolerances
+    atoms = mb.atoms_from_arrays(w["mass"], w["charge"], w["sigma"], w["eps"], dt_)
+    s = mb.System(atoms=atoms, coords=w["coords"].astype(dt_), boundary=mb.CubicBoundary(*w["box"]),
+                  pairwise_inters=(mb.CoulombEwald(dist_cutoff=0.9, error_tol=0.0005, use_neighbors=True),),
+                  neighbor_finder=mb.GPUNeighborFinder(dist_cutoff=0.9, excluded_pairs=w["excluded"] + 1),
+                  dtype=dt_, general_inters=(mb.PME(dist_cutoff=0.9, error_tol=0.0005, excluded_pairs=w["excluded"] + 1),))
+    f, e = mb.forces_energy(s)
+    err = np.linalg.norm(f - w["forces_pme"], axis=1).max()
+    print("water3", dt_.__name__, "max|dF| =", err, "dE =", e - float(w["energy_pme"]))
+    assert err < tol_f and abs(e - float(w["energy_pme"])) < tol_e
 """
 
 
 @pytest.mark.xfail(strict=False, reason="first implementation, never run on a GPU (round 1 budget was spent)")
 def test_6mrr_all_pme_on_device():
-    code = CHILD % dict(tests=os.path.join(ROOT, "tests"), root=ROOT, golden=os.path.join(ROOT, "tests", "golden", "6mrr.npz"))
+    code = CHILD % dict(tests=os.path.join(ROOT, "tests"), root=ROOT, golden=os.path.join(ROOT, "tests", "golden", "6mrr.npz"),
+                        water=os.path.join(ROOT, "tests", "golden", "water3.npz"))
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
     print(p.stdout[-2000:], p.stderr[-2000:])
     assert p.returncode == 0
