@@ -17,7 +17,9 @@
 
 namespace mb {
 
+#ifndef MB_HD
 #define MB_HD __host__ __device__ __forceinline__
+#endif
 
 constexpr int PME_ORDER = 5;
 constexpr int PME_THREADS = 128;
