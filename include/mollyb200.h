@@ -33,8 +33,10 @@ typedef struct mb_ctx mb_ctx;
 
 /* interaction kinds: src/interactions/lennard_jones.jl:28-35, coulomb.jl:32-70, :698-747, :1320-1394 */
 enum { MB_LJ = 0, MB_COULOMB = 1, MB_CRF = 2, MB_EWALD_REAL = 3 };
-/* cutoffs: src/cutoffs.jl:47-190 */
-enum { MB_CUT_NONE = 0, MB_CUT_DISTANCE = 1, MB_CUT_SHIFTED_POTENTIAL = 2, MB_CUT_SHIFTED_FORCE = 3 };
+/* cutoffs: src/cutoffs.jl:47-253. The two-point cutoffs (CubicSplineCutoff :174-215, PolynomialCutoff :217-253) take
+ * dist_activation in r_act and dist_cutoff in r_cut and apply to MB_LJ and MB_COULOMB. */
+enum { MB_CUT_NONE = 0, MB_CUT_DISTANCE = 1, MB_CUT_SHIFTED_POTENTIAL = 2, MB_CUT_SHIFTED_FORCE = 3,
+       MB_CUT_CUBIC_SPLINE = 4, MB_CUT_POLYNOMIAL = 5 };
 /* mixing rules: src/mixing.jl:20-38 */
 enum { MB_MIX_LORENTZ = 0, MB_MIX_GEOMETRIC = 1 };
 
@@ -52,14 +54,15 @@ typedef struct {
     int32_t kind;             /* MB_LJ | MB_COULOMB | MB_CRF | MB_EWALD_REAL */
     int32_t cutoff_kind;      /* MB_CUT_* (CRF / Ewald carry their own dist_cutoff in r_cut) */
     double r_cut;             /* inter.cutoff.dist_cutoff or inter.dist_cutoff */
-    double r_act;             /* reserved (dist_activation) */
+    double r_act;             /* inter.cutoff.dist_activation (MB_CUT_CUBIC_SPLINE / MB_CUT_POLYNOMIAL), else ignored */
     double weight_special;    /* inter.weight_special */
     double coulomb_const;     /* inter.coulomb_const (coulomb.jl:16) */
     double solvent_dielectric;/* CRF (coulomb.jl:676); +inf = conducting */
     double ewald_alpha;       /* CoulombEwald */
     int32_t sigma_mix;        /* MB_MIX_* for sigma (default Lorentz) */
     int32_t eps_mix;          /* MB_MIX_* for epsilon (default geometric) */
-    int32_t approx_erfc;      /* reserved */
+    int32_t approx_erfc;      /* CoulombEwald.approximate_erfc (coulomb.jl:1331, default true in the reference): erfc by
+                               * calc_erfc's 5-term polynomial (:1384-1393) instead of the exact function */
     int32_t use_neighbors;    /* inter.use_neighbors */
 } mb_inter_t;
 
@@ -135,12 +138,19 @@ int mb_forces_energy(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, vo
  * n_terms x 2 or 3. Host pointers. They are evaluated inside mb_simulate_vv (specific_forces_gpu!, src/force.jl:1231)
  * and by mb_forces_energy_all; mb_forces / mb_energy stay pairwise-only (the pairwise_*_loop_gpu! seam). */
 int mb_set_specific(mb_ctx* ctx, int kind, int64_t n_terms, const int32_t* atom_idx, const double* params);
-/* forces(sys) / potential_energy(sys) of pairwise + specific interactions in one call (ADD semantics). */
+/* forces(sys) / potential_energy(sys) of pairwise + specific + general interactions in one call (ADD semantics). */
 int mb_forces_energy_all(mb_ctx* ctx, const void* coords, void* fs_mat, void* pe, int64_t step_n);
 
-/* Particle-mesh Ewald, SURVEY.md §8(f)-3 — FIRST IMPLEMENTATION, not yet run on a GPU (its GPU parity test is marked
- * xfail). The arithmetic of its kernels is validated on the host (tests/test_pme_host.py: the __host__ __device__
- * per-item functions reproduce OpenMM's forces_all_pme_exact to < 1e-7 kJ/mol/nm), the plan by mb_pme_plan's test. Replaces the `PME`
+/* LJDispersionCorrection general interaction (src/interactions/lennard_jones.jl:163-275; added by setup.jl:2000-2004
+ * for cutoff systems): E = (factor_6 + factor_12) / V with the means of eps sigma^6, eps sigma^12 over all i <= j atom
+ * pairs (Lorentz sigma, geometric eps), no force, isotropic virial 2 U6 + 4 U12 on the diagonal. The factors are
+ * computed once on the host from the atoms (grouped by distinct (sigma, eps), double). dist_cutoff <= 0 switches it
+ * off. Added by mb_forces_energy_all (energy) — it is part of OpenMM's lj_only / all_cut energies. */
+int mb_set_lj_dispersion_correction(mb_ctx* ctx, double dist_cutoff);
+
+/* Particle-mesh Ewald, SURVEY.md §8(f)-3. GPU parity: tests/test_zz_gpu_pme.py (OpenMM forces_all_pme_exact at the
+ * reference's 1e-7 kJ/mol/nm / 1e-5 kJ/mol in f64); the per-item arithmetic is also checked on the host
+ * (tests/test_pme_host.py), the plan by mb_pme_plan's test. Replaces the `PME`
  * general interaction (src/interactions/ewald.jl:363-958; constructor PME(dist_cutoff, atoms, boundary; error_tol,
  * order=5, eps_r)) and the `EwaldExclusion` specific interaction list (:979-1055) that src/setup.jl:1903-1912 builds
  * from find_excluded_pairs(eligible, special): pairs = excluded OR special, 1-based. Use together with an
@@ -176,6 +186,15 @@ int mb_remove_cm_motion(mb_ctx* ctx, void* vels);
 /* kinetic_energy (src/energy.jl:56-70): writes 1/2 sum m v.v to *ke_host (double, host). */
 int mb_kinetic_energy(mb_ctx* ctx, const void* vels, double* ke_host);
 
+/* Kinetic energy tensor K = 1/2 sum m v (x) v (src/energy.jl:56-70; the reference copies masses and velocities to the
+ * host for it, :58-59): 3x3 symmetric, row-major == column-major, host doubles. */
+int mb_kinetic_energy_tensor(mb_ctx* ctx, const void* vels, double* ke_tensor9_host);
+/* random_velocities!(sys, temp; rng) (src/spatial.jl:819-831, GPU kernel src/kernels.jl:688-703): fills vels (n x 3, host
+ * or device) with Maxwell-Boltzmann velocities, sigma = sqrt(kT / m) per component, zero for massless atoms. Philox4x32-10
+ * keyed by the caller's two rand(rng, UInt64); statistical parity with the reference (its uniform -> normal transform
+ * lives in PhiloxRNG.jl, which is not vendored: SURVEY.md 8c). kT = k * temp in kJ/mol. */
+int mb_random_velocities(mb_ctx* ctx, void* vels, double kT, uint64_t rng_ctr1, uint64_t rng_key);
+
 /* find_neighbors(sys, nf, ..., force=true): force a rebuild from coords now (synchronous; also
  * re-derives capacities). */
 int mb_rebuild_neighbors(mb_ctx* ctx, const void* coords);
@@ -184,7 +203,7 @@ int mb_synchronize(mb_ctx* ctx);
 /* Multiply the auto-derived halo/list capacities (after MB_ERR_CAPACITY). */
 int mb_set_capacity_scale(mb_ctx* ctx, double scale);
 /* Tuning overrides (CUDALaunchConfig analogue, src/cuda_config.jl:27-41): brick dims in cells
- * (0 = auto), lanes per i-atom (4|8|16|32, 0 = auto). */
+ * (0 = auto), lanes per i-atom (8, or 0 = default; other values are rejected). */
 int mb_set_launch_config(mb_ctx* ctx, const int32_t brick_dims[3], int32_t lanes_per_atom);
 
 /* Per-kernel-category CUDA-event timing (benchmark_gpu_tiles.jl-style stage timers,

@@ -8,6 +8,7 @@
 #   Molly.pairwise_forces_loop_gpu!(buffers, sys, pairwise_inters, nbs::Nothing, Val(needs_vir), step_n)   ext:845
 #   Molly.pairwise_pe_loop_gpu!(pe_vec_nounits, buffers, sys, pairwise_inters, nbs::Nothing, step_n)        ext:936
 #   Molly.simulate!(sys, sim::VelocityVerlet, n_steps; ...)                                                 simulators.jl:547
+# (Molly.remove_CM_motion! for CuArray Systems is NOT redefined: the stock extension owns that exact signature)
 # and falls through to the stock methods (invoke) for anything it does not recognise: non-cubic boundaries,
 # constraints, virtual sites, couplings other than AndersenThermostat, interactions outside
 # {LennardJones, Coulomb, CoulombReactionField, CoulombEwald} or unsupported cutoffs / mixing rules.
@@ -49,6 +50,7 @@ end
 
 const MB_LJ, MB_COULOMB, MB_CRF, MB_EWALD_REAL = Int32(0), Int32(1), Int32(2), Int32(3)
 const MB_CUT_NONE, MB_CUT_DISTANCE, MB_CUT_SHIFTED_POTENTIAL, MB_CUT_SHIFTED_FORCE = Int32(0), Int32(1), Int32(2), Int32(3)
+const MB_CUT_CUBIC_SPLINE, MB_CUT_POLYNOMIAL = Int32(4), Int32(5)
 const MB_MIX_LORENTZ, MB_MIX_GEOMETRIC = Int32(0), Int32(1)
 
 function check(rc::Integer)
@@ -58,10 +60,13 @@ function check(rc::Integer)
 end
 
 # ---- translation of Molly interaction structs to descriptors -----------------------------------------
-cutoff_desc(::NoCutoff) = (MB_CUT_NONE, 0.0)
-cutoff_desc(c::DistanceCutoff) = (MB_CUT_DISTANCE, Float64(ustrip(c.dist_cutoff)))
-cutoff_desc(c::ShiftedPotentialCutoff) = (MB_CUT_SHIFTED_POTENTIAL, Float64(ustrip(c.dist_cutoff)))
-cutoff_desc(c::ShiftedForceCutoff) = (MB_CUT_SHIFTED_FORCE, Float64(ustrip(c.dist_cutoff)))
+# (kind, dist_cutoff, dist_activation)
+cutoff_desc(::NoCutoff) = (MB_CUT_NONE, 0.0, 0.0)
+cutoff_desc(c::DistanceCutoff) = (MB_CUT_DISTANCE, Float64(ustrip(c.dist_cutoff)), 0.0)
+cutoff_desc(c::ShiftedPotentialCutoff) = (MB_CUT_SHIFTED_POTENTIAL, Float64(ustrip(c.dist_cutoff)), 0.0)
+cutoff_desc(c::ShiftedForceCutoff) = (MB_CUT_SHIFTED_FORCE, Float64(ustrip(c.dist_cutoff)), 0.0)
+cutoff_desc(c::CubicSplineCutoff) = (MB_CUT_CUBIC_SPLINE, Float64(ustrip(c.dist_cutoff)), Float64(ustrip(c.dist_activation)))
+cutoff_desc(c::PolynomialCutoff) = (MB_CUT_POLYNOMIAL, Float64(ustrip(c.dist_cutoff)), Float64(ustrip(c.dist_activation)))
 cutoff_desc(::Any) = nothing
 
 mix_desc(::Molly.LorentzMixing) = MB_MIX_LORENTZ
@@ -73,19 +78,25 @@ function descriptor(inter::LennardJones)
     sm, em = mix_desc(inter.σ_mixing), mix_desc(inter.ϵ_mixing)
     (isnothing(cd) || isnothing(sm) || em != MB_MIX_GEOMETRIC) && return nothing
     !(inter.shortcut isa Molly.LJZeroShortcut) && return nothing
-    return MBInter(MB_LJ, cd[1], cd[2], 0.0, Float64(inter.weight_special), 138.93545764, 1.0, 0.0, sm, em, 0,
+    return MBInter(MB_LJ, cd[1], cd[2], cd[3], Float64(inter.weight_special), 138.93545764, 1.0, 0.0, sm, em, 0,
                    Int32(inter.use_neighbors))
 end
 function descriptor(inter::Coulomb)
     cd = cutoff_desc(inter.cutoff)
     isnothing(cd) && return nothing
-    return MBInter(MB_COULOMB, cd[1], cd[2], 0.0, Float64(inter.weight_special), Float64(ustrip(inter.coulomb_const)),
+    return MBInter(MB_COULOMB, cd[1], cd[2], cd[3], Float64(inter.weight_special), Float64(ustrip(inter.coulomb_const)),
                    1.0, 0.0, 0, 1, 0, Int32(inter.use_neighbors))
 end
 function descriptor(inter::CoulombReactionField)
     return MBInter(MB_CRF, MB_CUT_DISTANCE, Float64(ustrip(inter.dist_cutoff)), 0.0, Float64(inter.weight_special),
                    Float64(ustrip(inter.coulomb_const)), Float64(inter.solvent_dielectric), 0.0, 0, 1, 0,
                    Int32(inter.use_neighbors))
+end
+# CoulombEwald (src/interactions/coulomb.jl:1320-1441): alpha and approximate_erfc are fields of the struct
+function descriptor(inter::CoulombEwald)
+    return MBInter(MB_EWALD_REAL, MB_CUT_DISTANCE, Float64(ustrip(inter.dist_cutoff)), 0.0, Float64(inter.weight_special),
+                   Float64(ustrip(inter.coulomb_const)), 1.0, Float64(ustrip(inter.α)), 0, 1,
+                   Int32(inter.approximate_erfc), Int32(inter.use_neighbors))
 end
 descriptor(::Any) = nothing
 
@@ -142,7 +153,10 @@ function Molly.pairwise_forces_loop_gpu!(buffers, sys::System{3, <:CuArray, T}, 
                                          nbs::Nothing, ::Val{needs_vir}, step_n) where {T, needs_vir}
     descs = engine_eligible(sys, pairwise_inters)
     if isnothing(descs)
-        return invoke(Molly.pairwise_forces_loop_gpu!, Tuple{Any, System{3, <:CuArray, T}, Tuple, Nothing, Val, Any},
+        # the STOCK method's own signature (ext/MollyCUDAExt.jl:845: System{D, <:CuArray, T}, untyped pairwise_inters);
+        # naming this method's System{3, ...} signature here would recurse into itself
+        return invoke(Molly.pairwise_forces_loop_gpu!,
+                      Tuple{Any, System{D, <:CuArray, T} where D, Any, Nothing, Val{needs_vir}, Any},
                       buffers, sys, pairwise_inters, nbs, Val(needs_vir), step_n)
     end
     ctx = context_for(sys, descs)
@@ -157,7 +171,8 @@ function Molly.pairwise_pe_loop_gpu!(pe_vec_nounits, buffers, sys::System{3, <:C
                                      nbs::Nothing, step_n) where T
     descs = engine_eligible(sys, pairwise_inters)
     if isnothing(descs)
-        return invoke(Molly.pairwise_pe_loop_gpu!, Tuple{Any, Any, System{3, <:CuArray, T}, Tuple, Nothing, Any},
+        return invoke(Molly.pairwise_pe_loop_gpu!,   # stock: ext/MollyCUDAExt.jl:936
+                      Tuple{Any, Any, System{D, <:CuArray, T} where D, Any, Nothing, Any},
                       pe_vec_nounits, buffers, sys, pairwise_inters, nbs, step_n)
     end
     ctx = context_for(sys, descs)
@@ -228,7 +243,8 @@ end
 # Taken over only when nothing but the pairwise path contributes forces and nothing has to run on the host
 # every step; loggers fire between chunks of gcd(logger n_steps) steps (SURVEY.md Appendix A.11).
 function takeover_params(sys, sim::VelocityVerlet, n_steps, init_step, rng)
-    length(sys.general_inters) == 0 || return nothing
+    # LJDispersionCorrection adds no force (lennard_jones.jl:252-275); anything else (PME, implicit solvent) -> stock path
+    all(gi -> gi isa Molly.LJDispersionCorrection, sys.general_inters) || return nothing
     all(!isnothing, map(specific_desc, sys.specific_inter_lists)) || return nothing
     kT, prob = 0.0, 0.0
     couplings = sim.coupling isa Tuple ? sim.coupling : (sim.coupling,)
@@ -247,7 +263,8 @@ function Molly.simulate!(sys::System{3, <:CuArray, T}, sim::VelocityVerlet, n_st
     descs = engine_eligible(sys, sys.pairwise_inters)
     p = isnothing(descs) ? nothing : takeover_params(sys, sim, n_steps, init_step, rng)
     if isnothing(p)
-        return invoke(Molly.simulate!, Tuple{System, VelocityVerlet, Integer}, sys, sim, n_steps;
+        # stock: simulate!(sys, sim::VelocityVerlet, n_steps_or_time; ...) src/simulators.jl:547
+        return invoke(Molly.simulate!, Tuple{Any, VelocityVerlet, Any}, sys, sim, n_steps;
                       init_step=init_step, rng=rng, run_loggers=run_loggers, kwargs...)
     end
     ctx = context_for(sys, descs)
@@ -269,16 +286,19 @@ function Molly.simulate!(sys::System{3, <:CuArray, T}, sim::VelocityVerlet, n_st
 end
 
 # ---- remove_CM_motion! (ext/MollyCUDAExt.jl:2373) ---------------------------------------------------------
-function Molly.remove_CM_motion!(sys::System{3, <:CuArray, T}) where T
+# The stock extension's method has exactly the signature System{3, <:CuArray, T}; defining it again would be a method
+# overwrite (an error under precompilation). Inside the taken-over simulate! the engine removes the CM motion itself;
+# for stand-alone use this module offers its own function instead of replacing Molly's.
+function remove_cm_motion!(sys::System{3, <:CuArray, T}) where T
     descs = engine_eligible(sys, sys.pairwise_inters)
-    isnothing(descs) && return invoke(Molly.remove_CM_motion!, Tuple{System}, sys)
+    isnothing(descs) && return Molly.remove_CM_motion!(sys)
     ctx = context_for(sys, descs)
     check(ccall((:mb_remove_cm_motion, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}), ctx.handle, pointer(sys.velocities)))
     return sys
 end
 
-# The launch-config API of the stock extension stays callable (tests touch it, SURVEY.md §2 row 13):
-# optimize_cuda_launch_config! is a no-op here, the brick shape is chosen by the library (mb_set_launch_config).
-Molly.optimize_cuda_launch_config!(sys::System{3, <:CuArray}; kwargs...) = sys
+# The launch-config API of the stock extension (optimize_cuda_launch_config!, src/cuda_config.jl:53, ext:594) is left
+# alone: it tunes the stock kernels, which stay the fall-through path; the brick shape of this engine is chosen by the
+# library (mb_set_launch_config).
 
 end # module

@@ -9,6 +9,7 @@ LIB_PATH = os.environ.get("MOLLYB200_LIB") or os.path.join(_HERE, "libmollyb200.
 
 MB_LJ, MB_COULOMB, MB_CRF, MB_EWALD_REAL = 0, 1, 2, 3
 MB_CUT_NONE, MB_CUT_DISTANCE, MB_CUT_SHIFTED_POTENTIAL, MB_CUT_SHIFTED_FORCE = 0, 1, 2, 3
+MB_CUT_CUBIC_SPLINE, MB_CUT_POLYNOMIAL = 4, 5
 MB_MIX_LORENTZ, MB_MIX_GEOMETRIC = 0, 1
 MB_OK, MB_ERR_INVALID, MB_ERR_CUDA, MB_ERR_CAPACITY, MB_ERR_STATE, MB_ERR_NOGPU = 0, -1, -2, -3, -4, -5
 
@@ -18,6 +19,7 @@ EXPORTED = [
     "mb_forces_energy", "mb_simulate_vv", "mb_remove_cm_motion", "mb_kinetic_energy", "mb_rebuild_neighbors",
     "mb_stats", "mb_synchronize", "mb_set_capacity_scale", "mb_set_launch_config", "mb_comm_unique_id",
     "mb_comm_init", "mb_decomp_plan", "mb_set_profiling", "mb_set_specific", "mb_forces_energy_all", "mb_set_pme", "mb_pme_plan",
+    "mb_set_lj_dispersion_correction", "mb_random_velocities", "mb_kinetic_energy_tensor",
 ]
 
 
@@ -98,6 +100,9 @@ def load():
     L.mb_set_pme.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_double, i64, vp, vp]
     L.mb_pme_plan.argtypes = [vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, C.c_int]
     L.mb_forces_energy_all.argtypes = [vp, vp, vp, vp, i64]
+    L.mb_set_lj_dispersion_correction.argtypes = [vp, dbl]
+    L.mb_random_velocities.argtypes = [vp, vp, dbl, C.c_uint64, C.c_uint64]
+    L.mb_kinetic_energy_tensor.argtypes = [vp, vp, C.POINTER(dbl)]
     L.mb_decomp_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(i32), vp, C.POINTER(i32), C.c_int]
     L.mb_set_profiling.argtypes = [vp, C.c_int]
     for name in EXPORTED:

@@ -105,15 +105,42 @@ class ShiftedForceCutoff:
     dist_cutoff: float
 
 
+@dataclass
+class CubicSplineCutoff:
+    """CubicSplineCutoff(dist_activation, dist_cutoff) — src/cutoffs.jl:174-215."""
+    dist_activation: float
+    dist_cutoff: float
+
+    def __post_init__(self):
+        if self.dist_cutoff <= self.dist_activation:  # ArgumentError in the reference constructor (:181-187)
+            raise ValueError(f"the cutoff radius {self.dist_cutoff} must be larger than the activation radius {self.dist_activation}")
+
+
+@dataclass
+class PolynomialCutoff:
+    """PolynomialCutoff(dist_activation, dist_cutoff) — src/cutoffs.jl:217-253 (OpenMM's switching function)."""
+    dist_activation: float
+    dist_cutoff: float
+
+    def __post_init__(self):
+        if self.dist_cutoff <= self.dist_activation:
+            raise ValueError(f"the cutoff radius {self.dist_cutoff} must be larger than the activation radius {self.dist_activation}")
+
+
 def _cutoff_kind(c):
+    """-> (kind, dist_cutoff, dist_activation)"""
     if isinstance(c, NoCutoff):
-        return capi.MB_CUT_NONE, 0.0
+        return capi.MB_CUT_NONE, 0.0, 0.0
     if isinstance(c, DistanceCutoff):
-        return capi.MB_CUT_DISTANCE, c.dist_cutoff
+        return capi.MB_CUT_DISTANCE, c.dist_cutoff, 0.0
     if isinstance(c, ShiftedPotentialCutoff):
-        return capi.MB_CUT_SHIFTED_POTENTIAL, c.dist_cutoff
+        return capi.MB_CUT_SHIFTED_POTENTIAL, c.dist_cutoff, 0.0
     if isinstance(c, ShiftedForceCutoff):
-        return capi.MB_CUT_SHIFTED_FORCE, c.dist_cutoff
+        return capi.MB_CUT_SHIFTED_FORCE, c.dist_cutoff, 0.0
+    if isinstance(c, CubicSplineCutoff):
+        return capi.MB_CUT_CUBIC_SPLINE, c.dist_cutoff, c.dist_activation
+    if isinstance(c, PolynomialCutoff):
+        return capi.MB_CUT_POLYNOMIAL, c.dist_cutoff, c.dist_activation
     raise TypeError(f"unsupported cutoff {c!r}")
 
 
@@ -126,8 +153,8 @@ class LennardJones:
     eps_mixing: str = "geometric"
 
     def descriptor(self):
-        k, rc = _cutoff_kind(self.cutoff)
-        return capi.MBInter(capi.MB_LJ, k, rc, 0.0, self.weight_special, COULOMB_CONST, 1.0, 0.0,
+        k, rc, ra = _cutoff_kind(self.cutoff)
+        return capi.MBInter(capi.MB_LJ, k, rc, ra, self.weight_special, COULOMB_CONST, 1.0, 0.0,
                             capi.MB_MIX_GEOMETRIC if self.sigma_mixing == "geometric" else capi.MB_MIX_LORENTZ,
                             capi.MB_MIX_GEOMETRIC if self.eps_mixing == "geometric" else capi.MB_MIX_LORENTZ, 0,
                             int(self.use_neighbors))
@@ -141,8 +168,8 @@ class Coulomb:
     coulomb_const: float = COULOMB_CONST
 
     def descriptor(self):
-        k, rc = _cutoff_kind(self.cutoff)
-        return capi.MBInter(capi.MB_COULOMB, k, rc, 0.0, self.weight_special, self.coulomb_const, 1.0, 0.0, 0, 1, 0,
+        k, rc, ra = _cutoff_kind(self.cutoff)
+        return capi.MBInter(capi.MB_COULOMB, k, rc, ra, self.weight_special, self.coulomb_const, 1.0, 0.0, 0, 1, 0,
                             int(self.use_neighbors))
 
 
@@ -161,17 +188,19 @@ class CoulombReactionField:
 
 @dataclass
 class CoulombEwald:
-    """Real-space part of Ewald/PME (coulomb.jl:1320-1441); alpha = sqrt(-log(2 tol)) / dist_cutoff."""
+    """Real-space part of Ewald/PME (coulomb.jl:1320-1441); alpha = sqrt(-log(2 tol)) / dist_cutoff.
+    approximate_erfc=True (the reference's default, :1331) evaluates erfc with calc_erfc's polynomial (:1384-1393)."""
     dist_cutoff: float
     error_tol: float = 5e-4
     use_neighbors: bool = False
     weight_special: float = 1.0
     coulomb_const: float = COULOMB_CONST
+    approximate_erfc: bool = True
 
     def descriptor(self):
         alpha = np.sqrt(-np.log(2 * self.error_tol)) / self.dist_cutoff
         return capi.MBInter(capi.MB_EWALD_REAL, capi.MB_CUT_DISTANCE, self.dist_cutoff, 0.0, self.weight_special,
-                            self.coulomb_const, 1.0, float(alpha), 0, 1, 0, int(self.use_neighbors))
+                            self.coulomb_const, 1.0, float(alpha), 0, 1, int(self.approximate_erfc), int(self.use_neighbors))
 
 
 def _pairs_from(obj, n, want_true: bool):
@@ -217,6 +246,13 @@ class PME:
     order: int = 5
     eps_r: float = 1.0
     excluded_pairs: object = None
+
+
+@dataclass
+class LJDispersionCorrection:
+    """LJDispersionCorrection(atoms, dist_cutoff) general interaction (src/interactions/lennard_jones.jl:163-275): the
+    factors are computed by the library from the System's atoms."""
+    dist_cutoff: float
 
 
 @dataclass
@@ -365,8 +401,11 @@ class System:
             capi.check(L.mb_set_specific(ctx, kind, len(idx), idx.ctypes.data, par.ctypes.data))
 
         for gi in self.general_inters:
+            if isinstance(gi, LJDispersionCorrection):
+                capi.check(L.mb_set_lj_dispersion_correction(ctx, float(gi.dist_cutoff)))
+                continue
             if not isinstance(gi, PME):
-                raise ValueError("only PME is supported as a general interaction")
+                raise ValueError("only PME and LJDispersionCorrection are supported as general interactions")
             pairs = np.zeros((0, 2), np.int32) if gi.excluded_pairs is None else np.asarray(gi.excluded_pairs, np.int32).reshape(-1, 2)
             pi, pj = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
             self._keep_pme = (pi, pj)
@@ -415,12 +454,18 @@ def forces(sys: System, neighbors=None, step_n: int = 0) -> np.ndarray:
     """forces(sys[, neighbors, step_n]) — src/force.jl:678-687. Returns (n,3) in kJ mol^-1 nm^-1."""
     ctx = sys.engine()
     fs = np.zeros((sys.n, 3), sys.dtype)
-    capi.check(sys._L.mb_forces(ctx, _ptr(sys.coords), fs.ctypes.data, None, step_n))
+    if sys.specific_inter_lists or sys.general_inters:  # forces(sys) sums pairwise + specific + general interactions
+        capi.check(sys._L.mb_forces_energy_all(ctx, _ptr(sys.coords), fs.ctypes.data, None, step_n))
+    else:
+        capi.check(sys._L.mb_forces(ctx, _ptr(sys.coords), fs.ctypes.data, None, step_n))
     return fs
 
 
 def forces_virial(sys: System, neighbors=None, step_n: int = 0):
-    """forces_virial — src/force.jl:703-720. Returns (forces, virial 3x3)."""
+    """forces_virial — src/force.jl:703-720. Returns (forces, virial 3x3). Pairwise interactions only: a System with
+    specific or general interactions is refused instead of silently dropping their virial."""
+    if sys.specific_inter_lists or sys.general_inters:
+        raise NotImplementedError("forces_virial covers the pairwise seam (pairwise_forces_loop_gpu!) only")
     ctx = sys.engine()
     fs = np.zeros((sys.n, 3), sys.dtype)
     vir = np.zeros(9, sys.dtype)
@@ -432,7 +477,10 @@ def potential_energy(sys: System, neighbors=None, step_n: int = 0) -> float:
     """potential_energy(sys[, neighbors, step_n]) — src/energy.jl:202-248 (pairwise part)."""
     ctx = sys.engine()
     pe = np.zeros(1, sys.dtype)
-    capi.check(sys._L.mb_energy(ctx, _ptr(sys.coords), pe.ctypes.data, step_n))
+    if sys.specific_inter_lists or sys.general_inters:  # potential_energy(sys): pairwise + specific + general
+        capi.check(sys._L.mb_forces_energy_all(ctx, _ptr(sys.coords), None, pe.ctypes.data, step_n))
+    else:
+        capi.check(sys._L.mb_energy(ctx, _ptr(sys.coords), pe.ctypes.data, step_n))
     return float(pe[0])
 
 
@@ -511,10 +559,33 @@ def remove_CM_motion(sys: System):
 
 
 def random_velocities(sys: System, temp: float, rng=None) -> np.ndarray:
-    """Maxwell-Boltzmann velocities (src/spatial.jl:803-831); host-side setup helper."""
+    """random_velocities(sys, temp; rng) — src/spatial.jl:803-831: Maxwell-Boltzmann velocities drawn on the device
+    (Philox4x32-10 keyed by two 64-bit draws of `rng`, like the reference's GPU kernel src/kernels.jl:688-703)."""
     rng = rng or np.random.default_rng()
-    sd = np.sqrt(sys.k * temp / np.maximum(sys.masses, 1e-300))
-    return (rng.standard_normal((sys.n, 3)) * sd[:, None]).astype(sys.dtype)
+    ctx = sys.engine()
+    out = np.zeros((sys.n, 3), sys.dtype)
+    capi.check(sys._L.mb_random_velocities(ctx, out.ctypes.data, float(sys.k * temp), int(rng.integers(0, 2 ** 63)),
+                                           int(rng.integers(0, 2 ** 63))))
+    return out
+
+
+def random_velocities_(sys: System, temp: float, rng=None) -> System:
+    """random_velocities!(sys, temp): in place."""
+    v = random_velocities(sys, temp, rng)
+    if hasattr(sys.velocities, "data_ptr"):
+        import torch
+        sys.velocities.copy_(torch.from_numpy(v))
+    else:
+        sys.velocities[...] = v
+    return sys
+
+
+def kinetic_energy_tensor(sys: System) -> np.ndarray:
+    """K = 1/2 sum m v (x) v — src/energy.jl:56-70 (3x3, kJ/mol)."""
+    out = (C.c_double * 9)()
+    ctx = sys.engine()
+    capi.check(sys._L.mb_kinetic_energy_tensor(ctx, _ptr(sys.velocities), out))
+    return np.array(out[:], np.float64).reshape(3, 3)
 
 
 def wrap_coords(coords, boundary: CubicBoundary):

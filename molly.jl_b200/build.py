@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmollyb200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "pair.cuh", "cells.cuh", "force.cuh", "vv.cuh", os.path.join("..", "..", "include", "mollyb200.h")]
+# every header under csrc/ plus the C ABI header: an edit to any of them makes the library stale
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "mollyb200.h")]
 
 
 def _nvcc() -> str:

@@ -200,5 +200,11 @@ __global__ void sum_partials_kernel(int n, const double* __restrict__ partial, d
 
 template <typename T>
 __global__ void add_double_kernel(const double* src, T* dst) { *dst += (T)(*src); }
+// general interactions that are plain scalars (LJDispersionCorrection): pe += e; virial diagonal += w (column-major 3x3)
+template <typename T>
+__global__ void add_scalars_kernel(T* pe, T e, T* vir, T w) {
+    if (pe) *pe += e;
+    if (vir) { vir[0] += w; vir[4] += w; vir[8] += w; }
+}
 
 }  // namespace mb

@@ -1,11 +1,9 @@
 // cutoffs2.cuh — the two-point cutoffs CubicSplineCutoff and PolynomialCutoff.
 // Reference: src/cutoffs.jl:23-29, :39-45 (unchanged up to dist_activation, switched on (r_a, r_c], zero beyond),
 // :192-215 (cubic Hermite spline), :217-253 (5th-degree switching polynomial, OpenMM's switching function).
-// __host__ __device__ so that tests/test_pme_host.py-style host harnesses can check the arithmetic without a GPU
-// (tests/host/cutoffs_host.cu, tests/test_cutoffs_host.py). STATUS: prepared in round 1 after the GPU budget was spent
-// and NOT yet wired into pair.cuh: inlined into lj_term / coul_term it cost the validated ShiftedPotential /
-// ShiftedForce kernel variants 60-110 bytes of register spills each, out of line even more, and neither could be
-// measured any more. The C ABI therefore still rejects cutoff kinds 4 and 5; the oracle has them (oracle/molly_oracle_impl.h).
+// __host__ __device__ so that a host harness can check the arithmetic without a GPU (tests/host/cutoffs_host.cu,
+// tests/test_cutoffs_host.py). Used by pair.cuh's CUTM_TWO_POINT instantiations (lj_term / coul_term); the plain and
+// shifted kernel variants never see this code.
 #pragma once
 #include "common.cuh"
 

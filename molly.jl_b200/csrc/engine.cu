@@ -308,6 +308,9 @@ class EngineBase {
     virtual int comm_init(const void* uid, int rank, int nranks) = 0;
     virtual int set_specific(int kind, int64_t n, const int32_t* idx, const double* par) = 0;
     virtual int set_pme(double r_cut, double error_tol, int order, double eps_r, int64_t n_pairs, const int32_t* pi, const int32_t* pj) = 0;
+    virtual int set_dispersion(double r_cut) = 0;
+    virtual int random_velocities(void* vels, double kT, uint64_t ctr1, uint64_t key) = 0;
+    virtual int kinetic_tensor(const void* vels, double* out9) = 0;
 };
 
 template <typename T>
@@ -346,7 +349,7 @@ class Engine : public EngineBase {
         const size_t rec = (sizeof(T) == 4) ? 32 : 56;
         std::vector<unsigned char> host((size_t)n * rec);
         MB_CUDA(cudaMemcpy(host.data(), aos, host.size(), cudaMemcpyDefault));
-        h_mass_.resize(n); h_charge_.resize(n); h_sigma_.resize(n); h_eps_.resize(n);
+        h_mass_.resize(n); h_charge_.resize(n); h_sigma_.resize(n); h_eps_.resize(n); h_eps_raw_.resize(n);
         for (int64_t i = 0; i < n; i++) {
             const unsigned char* r = host.data() + (size_t)i * rec;
             T vals[5];
@@ -355,6 +358,7 @@ class Engine : public EngineBase {
             h_charge_[i] = vals[1];
             h_sigma_[i] = vals[2];
             h_eps_[i] = (vals[4] == (T)0) ? (T)0 : vals[3];  // lambda == 0 -> LJ zero shortcut (mixing.jl:7-11)
+            h_eps_raw_[i] = vals[3];
         }
         n_ = n;
         dirty_ = true;
@@ -368,6 +372,7 @@ class Engine : public EngineBase {
         MB_CUDA(cudaMemcpy(h_charge_.data(), charge, n * sizeof(T), cudaMemcpyDefault));
         MB_CUDA(cudaMemcpy(h_sigma_.data(), sigma, n * sizeof(T), cudaMemcpyDefault));
         MB_CUDA(cudaMemcpy(h_eps_.data(), eps, n * sizeof(T), cudaMemcpyDefault));
+        h_eps_raw_ = h_eps_;
         n_ = n;
         dirty_ = true;
         return MB_OK;
@@ -388,8 +393,15 @@ class Engine : public EngineBase {
             if (in[k].kind == MB_LJ) n_lj++;
             else if (in[k].kind == MB_COULOMB || in[k].kind == MB_CRF || in[k].kind == MB_EWALD_REAL) n_c++;
             else return set_error(MB_ERR_INVALID, "mb_set_inters: unknown interaction kind");
-            if (in[k].cutoff_kind < MB_CUT_NONE || in[k].cutoff_kind > MB_CUT_SHIFTED_FORCE)
+            if (in[k].cutoff_kind < MB_CUT_NONE || in[k].cutoff_kind > MB_CUT_POLYNOMIAL)
                 return set_error(MB_ERR_INVALID, "mb_set_inters: unsupported cutoff kind");
+            if (in[k].cutoff_kind >= MB_CUT_CUBIC_SPLINE) {
+                // CubicSplineCutoff / PolynomialCutoff constructors, src/cutoffs.jl:181-187, :239-245
+                if (in[k].kind != MB_LJ && in[k].kind != MB_COULOMB)
+                    return set_error(MB_ERR_INVALID, "mb_set_inters: two-point cutoffs apply to LennardJones and Coulomb only");
+                if (!(in[k].r_act > 0) || !(in[k].r_cut > in[k].r_act))
+                    return set_error(MB_ERR_INVALID, "mb_set_inters: the cutoff radius must be larger than the activation radius");
+            }
             if (in[k].kind == MB_LJ && in[k].eps_mix != MB_MIX_GEOMETRIC)
                 return set_error(MB_ERR_INVALID, "mb_set_inters: only geometric epsilon mixing is supported");
         }
@@ -453,8 +465,8 @@ class Engine : public EngineBase {
             if (bd[d] < 0 || bd[d] > 8) return set_error(MB_ERR_INVALID, "brick dims must be in 0..8");
             user_b_[d] = bd[d];
         }
-        if (!(lpa == 0 || lpa == 4 || lpa == 8 || lpa == 16 || lpa == 32))
-            return set_error(MB_ERR_INVALID, "lanes_per_atom must be 0, 4, 8, 16 or 32");
+        if (!(lpa == 0 || lpa == 8))
+            return set_error(MB_ERR_INVALID, "lanes_per_atom must be 0 (default) or 8: the 4- and 16-lane variants were measured slower and removed");
         lpa_ = lpa ? lpa : 8;
         have_list_ = false;
         dirty_ = true;
@@ -499,7 +511,7 @@ class Engine : public EngineBase {
         P_.coul_kind = COUL_NONE;
         P_.lj_rc2 = (T)0;
         P_.c_rc2 = (T)0;
-        shift_ = false;
+        cutm_ = CUTM_PLAIN;
         bool geo_sigma = false;
         for (auto& in : inters_) {
             // effective cutoff: NoCutoff with a neighbour list -> the finder radius (ext/MollyCUDAExt.jl:1691)
@@ -513,11 +525,13 @@ class Engine : public EngineBase {
             } else if (in.use_neighbors && r_list_ > 0) {
                 rc = r_list_;
             }
-            if (ck >= MB_CUT_SHIFTED_POTENTIAL) shift_ = true;
+            if (ck >= MB_CUT_CUBIC_SPLINE) cutm_ = CUTM_TWO_POINT;
+            else if (ck >= MB_CUT_SHIFTED_POTENTIAL && cutm_ == CUTM_PLAIN) cutm_ = CUTM_SHIFTED;
             if (in.kind == MB_LJ) {
                 P_.has_lj = 1;
                 P_.lj_cut_kind = ck;
                 P_.lj_rc = (T)rc; P_.lj_rc2 = (T)(rc * rc); P_.lj_inv_rc = (T)(1.0 / rc); P_.lj_inv_rc2 = (T)(1.0 / (rc * rc));
+                P_.lj_ra = (T)in.r_act; P_.lj_inv_ra2 = (in.r_act > 0) ? (T)(1.0 / (in.r_act * in.r_act)) : (T)0;
                 P_.lj_w14 = (T)in.weight_special;
                 P_.lj_nl = in.use_neighbors ? 1 : 0;
                 geo_sigma = (in.sigma_mix == MB_MIX_GEOMETRIC);
@@ -529,6 +543,8 @@ class Engine : public EngineBase {
                 P_.c_w14 = (T)in.weight_special;
                 P_.c_nl = in.use_neighbors ? 1 : 0;
                 P_.alpha = (T)in.ewald_alpha;
+                P_.c_ra = (T)in.r_act;
+                P_.approx_erfc = (in.kind == MB_EWALD_REAL && in.approx_erfc) ? 1 : 0;
                 if (in.kind == MB_CRF) {
                     double e = in.solvent_dielectric;
                     double krf, crf;
@@ -808,6 +824,38 @@ class Engine : public EngineBase {
         pme_on_ = true;
         pme_ready_ = false;
         destroy_graph();  // the captured step does not contain the PME launches
+        return MB_OK;
+    }
+    // ---- LJDispersionCorrection (general interaction; lennard_jones.jl:163-275) -----------------------------------
+    int set_dispersion(double r_cut) override {
+        if (r_cut < 0) return set_error(MB_ERR_INVALID, "mb_set_lj_dispersion_correction: negative cutoff");
+        disp_rc_ = r_cut;
+        disp_ready_ = false;
+        return MB_OK;
+    }
+    // factor_6 / factor_12 of the constructor (:170-226): means over all i <= j pairs, N (N + 1) / 2 terms, Lorentz sigma
+    // and geometric epsilon without the zero shortcut; accumulated in double, grouped by distinct (sigma, eps)
+    int dispersion_prepare() {
+        if (disp_ready_ || disp_rc_ <= 0) return MB_OK;
+        if (n_ <= 0) return set_error(MB_ERR_STATE, "LJ dispersion correction: atoms not set");
+        std::map<std::pair<double, double>, double> types;
+        for (int64_t i = 0; i < n_; i++) types[{(double)h_sigma_[i], (double)h_eps_raw_[i]}] += 1.0;
+        std::vector<std::pair<std::pair<double, double>, double>> tv(types.begin(), types.end());
+        double s6 = 0, s12 = 0;
+        for (size_t a = 0; a < tv.size(); a++)
+            for (size_t b = a; b < tv.size(); b++) {
+                const double np = (a == b) ? tv[a].second * (tv[a].second + 1.0) / 2.0 : tv[a].second * tv[b].second;
+                const double sig = (tv[a].first.first + tv[b].first.first) / 2.0;
+                const double e = std::sqrt(tv[a].first.second * tv[b].first.second);
+                const double sg6 = sig * sig * sig * sig * sig * sig;
+                s6 += np * e * sg6;
+                s12 += np * e * sg6 * sg6;
+            }
+        const double nd = (double)n_, n_pairs = nd * (nd + 1.0) / 2.0, pi_ = 3.14159265358979323846;
+        const double rc3 = disp_rc_ * disp_rc_ * disp_rc_;
+        disp_f6_ = 8.0 * pi_ * nd * nd * (-(s6 / n_pairs) / (3.0 * rc3));
+        disp_f12_ = 8.0 * pi_ * nd * nd * ((s12 / n_pairs) / (9.0 * rc3 * rc3 * rc3));
+        disp_ready_ = true;
         return MB_OK;
     }
     // grid dimensions, B-spline moduli, plan, self energy: ewald.jl:363-421 (constructor) and :947-956
@@ -1300,7 +1348,7 @@ class Engine : public EngineBase {
     }
 
     // ------------------------------------------------------------------------------------------
-    template <int COUL, bool UNIFORM, bool SHIFT, bool ENERGY>
+    template <int COUL, bool UNIFORM, int CUTM, bool ENERGY>
     int launch_force_t(ForceOut<T> out, int brick0, int nbr) {
         const size_t smem = force_smem_bytes();
         auto launch = [&](auto kern) -> int {
@@ -1314,11 +1362,7 @@ class Engine : public EngineBase {
             prof_.end(Prof::FORCE);
             return MB_OK;
         };
-        switch (lpa_) {
-            case 4: MB_TRY(launch(brick_force_kernel<T, COUL, UNIFORM, SHIFT, ENERGY, 4>)); break;
-            case 16: MB_TRY(launch(brick_force_kernel<T, COUL, UNIFORM, SHIFT, ENERGY, 16>)); break;
-            default: MB_TRY(launch(brick_force_kernel<T, COUL, UNIFORM, SHIFT, ENERGY, 8>)); break;
-        }
+        MB_TRY(launch(brick_force_kernel<T, COUL, UNIFORM, CUTM, ENERGY, 8>));
         launches_++;
         n_force_evals_++;
         MB_CUDA(cudaGetLastError());
@@ -1326,8 +1370,9 @@ class Engine : public EngineBase {
     }
     template <int COUL, bool UNIFORM>
     int launch_force_c(bool energy, ForceOut<T> out, int b0, int nbr) {
-        if (shift_) return energy ? launch_force_t<COUL, UNIFORM, true, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, true, false>(out, b0, nbr);
-        return energy ? launch_force_t<COUL, UNIFORM, false, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, false, false>(out, b0, nbr);
+        if (cutm_ == CUTM_TWO_POINT) return energy ? launch_force_t<COUL, UNIFORM, CUTM_TWO_POINT, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, CUTM_TWO_POINT, false>(out, b0, nbr);
+        if (cutm_ == CUTM_SHIFTED) return energy ? launch_force_t<COUL, UNIFORM, CUTM_SHIFTED, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, CUTM_SHIFTED, false>(out, b0, nbr);
+        return energy ? launch_force_t<COUL, UNIFORM, CUTM_PLAIN, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, CUTM_PLAIN, false>(out, b0, nbr);
     }
     // owned_only: in a decomposed run the step loop evaluates only this rank's slab of bricks
     int launch_force(bool energy, bool owned_only = false) {
@@ -1358,8 +1403,9 @@ class Engine : public EngineBase {
                                                                               ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), \
                                                                               sp_idx_dev(), f4, pe, vir)
         prof_.begin(Prof::FORCE);
-        if (shift_) { if (energy) MB_AP(true, true); else MB_AP(true, false); }
-        else { if (energy) MB_AP(false, true); else MB_AP(false, false); }
+        if (cutm_ == CUTM_TWO_POINT) { if (energy) MB_AP(CUTM_TWO_POINT, true); else MB_AP(CUTM_TWO_POINT, false); }
+        else if (cutm_ == CUTM_SHIFTED) { if (energy) MB_AP(CUTM_SHIFTED, true); else MB_AP(CUTM_SHIFTED, false); }
+        else { if (energy) MB_AP(CUTM_PLAIN, true); else MB_AP(CUTM_PLAIN, false); }
         prof_.end(Prof::FORCE);
 #undef MB_AP
         launches_++;
@@ -1493,6 +1539,13 @@ class Engine : public EngineBase {
             launches_++;
             if (with_specific && has_specific() && pe_target) {
                 add_double_kernel<T><<<1, 1, 0, stream_>>>(d_sp_energy_.as<double>(), pe_target);
+                launches_++;
+            }
+            if (with_specific && disp_rc_ > 0) {  // LJDispersionCorrection: E = (f6 + f12) / V; virial 2 U6 + 4 U12 on the diagonal
+                MB_TRY(dispersion_prepare());
+                const double vol = box_[0] * box_[1] * box_[2];
+                const double u6 = disp_f6_ / vol, u12 = disp_f12_ / vol;
+                add_scalars_kernel<T><<<1, 1, 0, stream_>>>(pe_target, (T)(u6 + u12), vir_target, (T)(2.0 * u6 + 4.0 * u12));
                 launches_++;
             }
             if ((pe && !pe_dev) || (vir && !vir_dev)) {
@@ -1881,6 +1934,43 @@ class Engine : public EngineBase {
         *out = s;
         return MB_OK;
     }
+    // kinetic energy tensor 1/2 sum m v (x) v (src/energy.jl:56-70) into out9 (3x3, symmetric, host doubles)
+    int kinetic_tensor(const void* vels, double* out9) override {
+        MB_TRY(prepare());
+        if (!vels || !out9) return set_error(MB_ERR_INVALID, "null argument");
+        const T* vc = nullptr;
+        MB_TRY(view_in(vels, 3 * (size_t)n_, d_stage_c_, &vc));
+        const int nb = (int)((n_ + 255) / 256);
+        MB_CUDA(d_partial_.ensure((size_t)nb * 6 * sizeof(double)));
+        kinetic_tensor_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, vc, d_mass_in_.as<T>(), d_partial_.as<double>());
+        launches_++;
+        std::vector<double> part((size_t)nb * 6);
+        MB_CUDA(cudaMemcpyAsync(part.data(), d_partial_.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        double k[6] = {0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < nb; b++) for (int d = 0; d < 6; d++) k[d] += part[6 * (size_t)b + d];
+        out9[0] = k[0]; out9[4] = k[1]; out9[8] = k[2];
+        out9[1] = out9[3] = k[3]; out9[2] = out9[6] = k[4]; out9[5] = out9[7] = k[5];
+        return MB_OK;
+    }
+    // random_velocities!(sys, temp; rng) on the device (src/spatial.jl:819-831): fills vels (n x 3, host or device)
+    int random_velocities(void* vels, double kT, uint64_t ctr1, uint64_t key) override {
+        MB_TRY(prepare());
+        if (!vels || !(kT >= 0)) return set_error(MB_ERR_INVALID, "mb_random_velocities: null velocities or negative kT");
+        const bool dev = is_device_ptr(vels);
+        T* vo = reinterpret_cast<T*>(vels);
+        if (!dev) {
+            MB_CUDA(d_stage_c_.ensure(3 * (size_t)n_ * sizeof(T)));
+            vo = d_stage_c_.as<T>();
+        }
+        const int nb = (int)((n_ + 255) / 256);
+        random_velocities_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, (T)kT, d_mass_in_.as<T>(), (uint32_t)ctr1, (uint32_t)(ctr1 >> 32),
+                                                             (uint32_t)key, (uint32_t)(key >> 32), vo);
+        launches_++;
+        if (!dev) MB_CUDA(cudaMemcpyAsync(vels, vo, 3 * (size_t)n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+        MB_CUDA(cudaStreamSynchronize(stream_));
+        return MB_OK;
+    }
     int rebuild(const void* coords) override {
         MB_TRY(prepare());
         if (path_ == 0) return MB_OK;
@@ -1932,7 +2022,9 @@ class Engine : public EngineBase {
     int sm_count_ = 148;
     size_t smem_optin_ = 232448;
     int64_t n_ = 0;
-    std::vector<T> h_mass_, h_charge_, h_sigma_, h_eps_;
+    std::vector<T> h_mass_, h_charge_, h_sigma_, h_eps_, h_eps_raw_;
+    double disp_rc_ = 0, disp_f6_ = 0, disp_f12_ = 0;  // LJDispersionCorrection (0 = off)
+    bool disp_ready_ = false;
     double box_[3];
     std::vector<mb_inter_t> inters_;
     std::vector<int> ex_ptr_, ex_idx_, sp_ptr_, sp_idx_;
@@ -1941,7 +2033,8 @@ class Engine : public EngineBase {
     int rebuild_every_ = 0;
     int user_b_[3] = {0, 0, 0};
     int lpa_ = 8;
-    bool dirty_ = true, have_list_ = false, slots_init_ = false, shift_ = false;
+    bool dirty_ = true, have_list_ = false, slots_init_ = false;
+    int cutm_ = CUTM_PLAIN;  // cutoff family of the kernel variant (pair.cuh)
     int path_ = 0;
     PairParams<T> P_;
     Geom<T> g_, g_ap_;
@@ -2091,6 +2184,12 @@ int mb_set_pme(mb_ctx* ctx, double r_cut, double error_tol, int order, double ep
     MB_CTX_GUARD(ctx);
     return ctx->e->set_pme(r_cut, error_tol, order, eps_r, n_pairs, pi, pj);
 }
+int mb_set_lj_dispersion_correction(mb_ctx* ctx, double dist_cutoff) { MB_CTX_GUARD(ctx); return ctx->e->set_dispersion(dist_cutoff); }
+int mb_random_velocities(mb_ctx* ctx, void* vels, double kT, uint64_t rng_ctr1, uint64_t rng_key) {
+    MB_CTX_GUARD(ctx);
+    return ctx->e->random_velocities(vels, kT, rng_ctr1, rng_key);
+}
+int mb_kinetic_energy_tensor(mb_ctx* ctx, const void* vels, double* ke_tensor9_host) { MB_CTX_GUARD(ctx); return ctx->e->kinetic_tensor(vels, ke_tensor9_host); }
 int mb_simulate_vv(mb_ctx* ctx, void* coords, void* vels, const mb_vv_params_t* p) { MB_CTX_GUARD(ctx); return ctx->e->simulate_vv(coords, vels, p); }
 int mb_remove_cm_motion(mb_ctx* ctx, void* vels) { MB_CTX_GUARD(ctx); return ctx->e->remove_cm(vels); }
 int mb_kinetic_energy(mb_ctx* ctx, const void* vels, double* ke_host) { MB_CTX_GUARD(ctx); return ctx->e->kinetic_energy(vels, ke_host); }

@@ -38,8 +38,9 @@ struct ForceOut {
     PeerWait gate;            // decomposed run over peer memory: epoch flags the halo data of this step arrives under
 };
 
-template <typename T, int COUL, bool UNIFORM, bool SHIFT, bool ENERGY, int LPA>
-__global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
+// f64 variants get half the resident CTAs (128 registers): under the f32 bound of 64 they spilled 560-1113 LDL/STL each
+template <typename T, int COUL, bool UNIFORM, int CUTM, bool ENERGY, int LPA>
+__global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 2 : MB_MIN_BLOCKS)
     brick_force_kernel(Geom<T> g, PairParams<T> P, const BrickHdr* __restrict__ hdrs, const Run* __restrict__ runs,
                        const IRow* __restrict__ irows, const typename VT<T>::T4* __restrict__ pos4,
                        const typename VT<T>::T2* __restrict__ lj2, const unsigned short* __restrict__ list,
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
             const T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
             const T r2 = dx * dx + dy * dy + dz * dz;
             T fr, e;
-            pair_eval<T, COUL, UNIFORM, SHIFT, ENERGY, SPECIAL>(P, r2, lj_s_i, lj_e_i, lj_s_j, lj_e_j, kq_i, pj.w, fr, e);
+            pair_eval<T, COUL, UNIFORM, CUTM, ENERGY, SPECIAL>(P, r2, lj_s_i, lj_e_i, lj_s_j, lj_e_j, kq_i, pj.w, fr, e);
             const T gx = fr * dx, gy = fr * dy, gz = fr * dz;
             fx += gx;
             fy += gy;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
                     lj[u] = *reinterpret_cast<const T2*>(reinterpret_cast<const char*>(s_lj) + (((size_t)j[u] * sizeof(T2)) >> LIST_SHIFT));
             }
 #if MB_USE_F32X2
-            if constexpr (std::is_same<T, float>::value && UNIFORM && !SHIFT && !ENERGY && COUL == COUL_NONE) {
+            if constexpr (std::is_same<T, float>::value && UNIFORM && CUTM == CUTM_PLAIN && !ENERGY && COUL == COUL_NONE) {
                 // Blackwell packed-f32 path (FADD2 / FMUL2 / FFMA2): two neighbours per instruction
 #pragma unroll
                 for (int h2 = 0; h2 < 2; h2++) {
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, MB_MIN_BLOCKS)
             }
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                pair_eval<T, COUL, UNIFORM, SHIFT, ENERGY, false>(P, r2[u], lj_s_i, lj_e_i, UNIFORM ? (T)0 : lj[u].x,
+                pair_eval<T, COUL, UNIFORM, CUTM, ENERGY, false>(P, r2[u], lj_s_i, lj_e_i, UNIFORM ? (T)0 : lj[u].x,
                                                                   UNIFORM ? (T)0 : lj[u].y, kq_i, pj[u].w, fr[u], e[u]);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -376,7 +377,7 @@ __device__ __forceinline__ T mic_1d(T ci, T cj, T L) {
 
 constexpr int AP_THREADS = 128;
 
-template <typename T, int COUL, bool SHIFT, bool ENERGY>
+template <typename T, int COUL, int CUTM, bool ENERGY>
 __global__ void __launch_bounds__(AP_THREADS)
     allpairs_force_kernel(int n, PairParams<T> P, T Lx, T Ly, T Lz, const typename VT<T>::T4* __restrict__ posq,
                           const typename VT<T>::T2* __restrict__ lj2, const int* __restrict__ ex_ptr,
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(AP_THREADS)
             T dx = -mic_1d(pi.x, pj.x, Lx), dy = -mic_1d(pi.y, pj.y, Ly), dz = -mic_1d(pi.z, pj.z, Lz);
             T r2 = dx * dx + dy * dy + dz * dz;
             T fr, e;
-            pair_eval_rt<T, COUL, SHIFT, ENERGY>(P, r2, li.x, li.y, lj.x, lj.y, kq_i, pj.w, excluded, special, fr, e);
+            pair_eval_rt<T, COUL, CUTM, ENERGY>(P, r2, li.x, li.y, lj.x, lj.y, kq_i, pj.w, excluded, special, fr, e);
             T gx = fr * dx, gy = fr * dy, gz = fr * dz;
             fx += gx; fy += gy; fz += gz;
             if (ENERGY) {

@@ -426,6 +426,51 @@ __global__ void kinetic_kernel(int n, const T* __restrict__ vels, const T* __res
     }
 }
 
+// kinetic energy tensor K = 1/2 sum m v (x) v (src/energy.jl:56-70): xx, yy, zz, xy, xz, yz partials per CTA
+template <typename T>
+__global__ void kinetic_tensor_kernel(int n, const T* __restrict__ vels, const T* __restrict__ mass, double* __restrict__ partial) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double k[6] = {0, 0, 0, 0, 0, 0};
+    if (i < n) {
+        const double m = 0.5 * (double)mass[i];
+        const double vx = vels[3 * (size_t)i], vy = vels[3 * (size_t)i + 1], vz = vels[3 * (size_t)i + 2];
+        k[0] = m * vx * vx; k[1] = m * vy * vy; k[2] = m * vz * vz; k[3] = m * vx * vy; k[4] = m * vx * vz; k[5] = m * vy * vz;
+    }
+    __shared__ double s_red[32][6];
+    for (int d = 0; d < 6; d++)
+        for (int o = 16; o > 0; o >>= 1) k[d] += __shfl_xor_sync(0xffffffffu, k[d], o);
+    if ((threadIdx.x & 31) == 0)
+        for (int d = 0; d < 6; d++) s_red[threadIdx.x >> 5][d] = k[d];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += s_red[w][threadIdx.x];
+        partial[6 * (size_t)blockIdx.x + threadIdx.x] = s;
+    }
+}
+
+// random_velocities! (src/spatial.jl:803-831; GPU kernel src/kernels.jl:688-703): every atom gets a Maxwell-Boltzmann
+// velocity, sigma_v = sqrt(kT / m) per component (massless / virtual sites: zero). Philox4x32-10, counter = 1-based atom
+// index, (ctr1, key) = the caller's two rand(rng, UInt64); normals by Box-Muller. Statistical parity only (SURVEY §8c:
+// the reference's uniform -> normal transform lives in the un-vendored PhiloxRNG.jl).
+template <typename T>
+__global__ void random_velocities_kernel(int n, T kT, const T* __restrict__ mass, uint32_t ctr1_lo, uint32_t ctr1_hi,
+                                         uint32_t key_lo, uint32_t key_hi, T* __restrict__ vels) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t d[4] = {(uint32_t)(i + 1), 0u, ctr1_lo, ctr1_hi};
+    philox4x32_10(d, key_lo, key_hi);
+    const double two_pi = 6.283185307179586;
+    const double u1 = ((double)d[0] + 1.0) * (1.0 / 4294967296.0), u2 = (double)d[1] * (1.0 / 4294967296.0);
+    const double u3 = ((double)d[2] + 1.0) * (1.0 / 4294967296.0), u4 = (double)d[3] * (1.0 / 4294967296.0);
+    const double r1 = sqrt(-2.0 * log(u1)), r2 = sqrt(-2.0 * log(u3));
+    const T m = mass[i];
+    const double sd = (m > (T)0) ? sqrt((double)kT / (double)m) : 0.0;
+    vels[3 * (size_t)i] = (T)(sd * r1 * cos(two_pi * u2));
+    vels[3 * (size_t)i + 1] = (T)(sd * r1 * sin(two_pi * u2));
+    vels[3 * (size_t)i + 2] = (T)(sd * r2 * cos(two_pi * u4));
+}
+
 // sum(m v) partials over an original-order velocity array (mb_remove_cm_motion)
 template <typename T>
 __global__ void momentum_kernel(int n, const T* __restrict__ vels, const T* __restrict__ mass, double* __restrict__ partial) {

@@ -38,6 +38,9 @@ def main():
                  "all_pme_exact", "all_pme"):
         out[f"forces_{name}"] = np.loadtxt(f"{amber}/forces_{name}.txt")
         out[f"energy_{name}"] = np.float64(open(f"{amber}/energy_{name}.txt").read())
+    # 100 VelocityVerlet steps of the :pme system from velocities_300K (test/protein.jl:277-299: 1e-10 nm, 1e-7 nm/ps)
+    out["coordinates_100steps"] = np.loadtxt(f"{amber}/coordinates_100steps.txt")
+    out["velocities_100steps"] = np.loadtxt(f"{amber}/velocities_100steps.txt")
     np.savez_compressed(os.path.join(OUT, "6mrr.npz"), **out)
     print("wrote", os.path.join(OUT, "6mrr.npz"), os.path.getsize(os.path.join(OUT, "6mrr.npz")) / 1e6, "MB")
     water3()

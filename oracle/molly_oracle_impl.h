@@ -70,7 +70,7 @@ typedef struct {
  * LJ:       src/interactions/lennard_jones.jl:79-140, mixing src/mixing.jl:5-34
  * Coulomb:  src/interactions/coulomb.jl:71-120
  * CRF:      src/interactions/coulomb.jl:748-814
- * Ewald-real: src/interactions/coulomb.jl:1395-1441 (exact erfc)
+ * Ewald-real: src/interactions/coulomb.jl:1395-1441; erfc exact or calc_erfc's polynomial (:1384-1393) per approx_erfc
  * cutoffs:  src/cutoffs.jl:15-45 (NoCutoff / DistanceCutoff),
  *           :99-141 (ShiftedPotential), :143-190 (ShiftedForce), :192-253 (CubicSpline, Polynomial; LJ only)
  */
@@ -194,8 +194,15 @@ static inline void FN(pair_eval)(const orc_inter_t *in, const FN(pairparm) * p, 
         } else {
             double a = in->ewald_alpha;
             double ar = a * (double)r;
-            double erfc_ar = erfc(ar);
             double ex = exp(-ar * ar);
+            double erfc_ar;
+            if (in->approx_erfc) {
+                /* calc_erfc, coulomb.jl:1384-1393: Abramowitz & Stegun 7.1.26 (the reference's default) */
+                double t = 1.0 / (1.0 + 0.3275911 * ar);
+                erfc_ar = (0.254829592 + (-0.284496736 + (1.421413741 + (-1.453152027 + 1.061405429 * t) * t) * t) * t) * t * ex;
+            } else {
+                erfc_ar = erfc(ar);
+            }
             REAL f = (REAL)((double)kqq * (erfc_ar + 2.0 * ar * ex / 1.7724538509055160273) /
                             ((double)r2 * (double)r));
             REAL e = (REAL)((double)kqq * erfc_ar / (double)r);

@@ -127,10 +127,11 @@ class Inter:
     sigma_mix: int = MIX_LORENTZ
     eps_mix: int = MIX_GEOMETRIC
     use_neighbors: bool = False
+    approx_erfc: bool = False  # CoulombEwald(approximate_erfc=...), coulomb.jl:1331 (reference default: true)
 
     def to_c(self) -> InterC:
         return InterC(self.kind, self.cutoff_kind, self.r_cut, self.r_act, self.weight_special, self.coulomb_const,
-                      self.solvent_dielectric, self.ewald_alpha, self.sigma_mix, self.eps_mix, 0,
+                      self.solvent_dielectric, self.ewald_alpha, self.sigma_mix, self.eps_mix, int(self.approx_erfc),
                       int(self.use_neighbors))
 
 

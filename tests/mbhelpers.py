@@ -137,7 +137,7 @@ def sixmrr_specific_lists(g):
             mb.InteractionList4Atoms(t[:, 0], t[:, 1], t[:, 2], t[:, 3], tp[:, 0], tp[:, 1], tp[:, 2]))
 
 
-def sixmrr_system(g, dtype, r_list=1.2, n_steps=0, bonded=True, coords=None, velocities=None, device=0):
+def sixmrr_system(g, dtype, r_list=1.2, n_steps=0, bonded=True, coords=None, velocities=None, device=0, dispersion=False):
     """System(6mrr_equil.pdb, ff99SBildn + tip3p; nonbonded_method=:cutoff) as benchmark/protein.jl:24-37 builds it:
     LJ(rc 1.0, w14 0.5) + CoulombReactionField(rc 1.0, eps 78.3, w14 0.8333) + bonds/angles/torsions."""
     import mollyb200 as mb
@@ -150,7 +150,8 @@ def sixmrr_system(g, dtype, r_list=1.2, n_steps=0, bonded=True, coords=None, vel
     v = sd["velocities"] if velocities is None else velocities
     return mb.System(atoms=atoms, coords=np.asarray(x).astype(dtype), boundary=mb.CubicBoundary(*sd["box"]),
                      velocities=np.asarray(v).astype(dtype), pairwise_inters=inters, neighbor_finder=nf, dtype=dtype,
-                     specific_inter_lists=sixmrr_specific_lists(g) if bonded else (), device=device)
+                     specific_inter_lists=sixmrr_specific_lists(g) if bonded else (), device=device,
+                     general_inters=(mb.LJDispersionCorrection(1.0),) if dispersion else ())  # setup.jl:2000-2004
 
 
 def sixmrr_oracle(g, dtype=np.float64):
@@ -197,3 +198,55 @@ def oracle_vv_with_bonded(g, x, v, dt, n_steps, r_list=1.2, nl_every=10):
         if step % nl_every == 0:
             nl = orc.neighbor_list(x, r_list)
     return x, v
+
+
+def oracle_vv_pme(g, x, v, dt, n_steps, r_list=1.2, nl_every=10):
+    """simulate!(sys_pme_exact, VelocityVerlet(dt), n) of test/protein.jl:277-299 restated with the oracle's pieces (f64):
+    LJ + CoulombEwald real space (C oracle over the neighbour list) + bonded + EwaldExclusion + PME reciprocal space
+    (oracle/pme.py, numpy), remove_CM_motion = 1."""
+    from oracle import oracle as o, pme
+    sd = sixmrr_description(g)
+    box, m = sd["box"], sd["mass"]
+    alpha = pme.pme_alpha(1.0)
+    inters = [o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=float(g["lj14scale"]), use_neighbors=True),
+              o.Inter(o.EWALD_REAL, o.CUT_DISTANCE, 1.0, weight_special=float(g["coulomb14scale"]), ewald_alpha=alpha,
+                      use_neighbors=True)]
+    orc = make_oracle(sd, inters)
+    excl = np.concatenate([g["excluded"], g["special"]])
+    x = x - np.floor(x / box) * box
+    v = orc.remove_cm(v)
+
+    def forces(xx, nl):
+        f, _, _ = orc.forces_nl(xx, nl, energy=False)
+        fr, _, _ = pme.pme_reciprocal(xx, g["charge"], box, r_cut=1.0, error_tol=0.0005, order=5)
+        fx, _ = pme.ewald_exclusion(xx, g["charge"], box, excl)
+        return f + fr + fx + bonded_forces_oracle(g, xx)[0]
+    nl = orc.neighbor_list(x, r_list)
+    f = forces(x, nl)
+    for step in range(1, n_steps + 1):
+        v = v + f / m[:, None] * (dt / 2)
+        x = x + v * dt
+        x = x - np.floor(x / box) * box
+        f = forces(x, nl)
+        v = v + f / m[:, None] * (dt / 2)
+        v = orc.remove_cm(v)
+        if step % nl_every == 0:
+            nl = orc.neighbor_list(x, r_list)
+    return x, v
+
+
+def sixmrr_pme_system(g, dtype, r_list=1.2, exact=True, velocities=None):
+    """System(6mrr; nonbonded_method=:pme, approximate_pme=!exact) of test/protein.jl:76-85 / setup.jl:1894-1927: LJ +
+    CoulombEwald + bonded lists + PME + EwaldExclusion(excluded or special) + LJDispersionCorrection."""
+    import mollyb200 as mb
+    sd = sixmrr_description(g)
+    atoms = mb.atoms_from_arrays(sd["mass"], sd["charge"], sd["sigma"], sd["eps"], dtype)
+    inters = (mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True, weight_special=float(g["lj14scale"])),
+              mb.CoulombEwald(dist_cutoff=1.0, error_tol=0.0005, use_neighbors=True, weight_special=float(g["coulomb14scale"]),
+                              approximate_erfc=not exact))
+    nf = mb.GPUNeighborFinder(dist_cutoff=r_list, excluded_pairs=g["excluded"] + 1, special_pairs=g["special"] + 1)
+    pme = mb.PME(dist_cutoff=1.0, error_tol=0.0005, excluded_pairs=np.concatenate([g["excluded"], g["special"]]) + 1)
+    v = sd["velocities"] if velocities is None else velocities
+    return mb.System(atoms=atoms, coords=sd["coords"].astype(dtype), boundary=mb.CubicBoundary(*sd["box"]),
+                     velocities=np.asarray(v).astype(dtype), pairwise_inters=inters, neighbor_finder=nf, dtype=dtype,
+                     specific_inter_lists=sixmrr_specific_lists(g), general_inters=(pme, mb.LJDispersionCorrection(1.0)))

@@ -64,6 +64,13 @@ def _cutoff_force_bound(sysd, o_inters):
     return b
 
 
+def _pairwise_forces(s):
+    """pairwise_forces_loop_gpu! seam only (mb_forces), whatever else the System carries."""
+    fs = np.zeros((s.n, 3), s.dtype)
+    mb.capi.check(s._L.mb_forces(s.engine(), s.coords.ctypes.data, fs.ctypes.data, None, 0))
+    return fs
+
+
 def _check(sysd, mb_inters, o_inters, dtype, r_list=0.0, expect_path=None, label=""):
     xin = sysd["coords"].astype(dtype)
     sd = dict(sysd, coords=xin)
@@ -183,7 +190,7 @@ def test_lj_fluid_16k(dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("coul", ["crf", "coulomb_sf", "ewald"])
+@pytest.mark.parametrize("coul", ["crf", "coulomb_sf", "ewald", "ewald_approx"])
 def test_molecular_brick_path(dtype, coul):
     sd = H.molecular_system(1000, [5.1, 5.4, 5.8], seed=5)  # 4000 atoms, orthorhombic, mixed types, charges
     lj_m = mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True, weight_special=0.5)
@@ -195,9 +202,11 @@ def test_molecular_brick_path(dtype, coul):
         c_m = mb.Coulomb(cutoff=mb.ShiftedForceCutoff(1.0), use_neighbors=True, weight_special=0.8333)
         c_o = o.Inter(o.COULOMB, o.CUT_SHIFTED_FORCE, 1.0, weight_special=0.8333, use_neighbors=True)
     else:
-        c_m = mb.CoulombEwald(dist_cutoff=1.0, use_neighbors=True, weight_special=0.8333)
+        approx = coul == "ewald_approx"  # approximate_erfc=true is the reference's default (coulomb.jl:1331)
+        c_m = mb.CoulombEwald(dist_cutoff=1.0, use_neighbors=True, weight_special=0.8333, approximate_erfc=approx)
         alpha = float(np.sqrt(-np.log(2 * 5e-4)) / 1.0)
-        c_o = o.Inter(o.EWALD_REAL, o.CUT_DISTANCE, 1.0, weight_special=0.8333, ewald_alpha=alpha, use_neighbors=True)
+        c_o = o.Inter(o.EWALD_REAL, o.CUT_DISTANCE, 1.0, weight_special=0.8333, ewald_alpha=alpha, use_neighbors=True,
+                      approx_erfc=approx)
     _check(sd, (lj_m, c_m), [lj_o, c_o], dtype, r_list=1.1, expect_path=1, label=f"molecular brick {coul}")
 
 
@@ -213,13 +222,17 @@ def test_6mrr_openmm_golden_f64(golden_6mrr, name):
         inter = mb.CoulombReactionField(dist_cutoff=1.0, use_neighbors=True, weight_special=float(g["coulomb14scale"]))
     atoms = mb.atoms_from_arrays(g["mass"], g["charge"], g["sigma"], g["eps"], np.float64)
     nf = mb.GPUNeighborFinder(dist_cutoff=1.2, excluded_pairs=g["excluded"] + 1, special_pairs=g["special"] + 1)
+    # lj_only carries sys.general_inters = (LJDispersionCorrection,) in the reference's test (test/protein.jl:247-248)
+    gis = (mb.LJDispersionCorrection(1.0),) if name == "lj_only" else ()
     s = mb.System(atoms=atoms, coords=x, boundary=mb.CubicBoundary(*box), pairwise_inters=(inter,), neighbor_finder=nf,
-                  dtype=np.float64)
+                  dtype=np.float64, general_inters=gis)
     f = mb.forces(s)
     e = mb.potential_energy(s)
     st = s.stats()
-    if name == "lj_only":
-        e += o.lj_dispersion_correction_energy(g["sigma"], g["eps"], box, 1.0)  # general interaction, host scalar
+    if name == "lj_only":  # the product's correction equals the oracle's restatement of the constructor
+        e_pair = np.zeros(1)
+        mb.capi.check(s._L.mb_energy(s.engine(), s.coords.ctypes.data, e_pair.ctypes.data, 0))
+        assert abs((e - e_pair[0]) - o.lj_dispersion_correction_energy(g["sigma"], g["eps"], box, 1.0)) < 1e-9
     err = np.linalg.norm(f - g[f"forces_{name}"], axis=1).max()
     print(f"[6mrr {name}] path={st['path']} brick={st['brick_dims']} maxnb={st['max_neighbors']} "
           f"pairs={st['n_pairs_in_list']} max|dF|={err:.3e} dE={e - float(g[f'energy_{name}']):.3e}")
@@ -276,15 +289,16 @@ def test_6mrr_all_cut_openmm_golden_f64(golden_6mrr):
     """LJ + CRF + HarmonicBond + HarmonicAngle + PeriodicTorsion (propers + impropers) on the GPU vs OpenMM's
     forces_all_cut / energy_all_cut (test/protein.jl:263-275: 1e-7 kJ/mol/nm, 1e-5 kJ/mol)."""
     g = golden_6mrr
-    s = H.sixmrr_system(g, np.float64, r_list=1.2)
+    s = H.sixmrr_system(g, np.float64, r_list=1.2, dispersion=True)
     f, e = mb.forces_energy(s)
-    e += o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
     err = np.linalg.norm(f - g["forces_all_cut"], axis=1).max()
     print(f"[6mrr all_cut f64] max|dF|={err:.3e} dE={e - float(g['energy_all_cut']):.3e}")
     assert err < 1e-7
     assert abs(e - float(g["energy_all_cut"])) < 1e-5
-    # bonded-only parity: pairwise-only call subtracted
-    f_pair = mb.forces(s)
+    # forces(sys) / potential_energy(sys) route through the same all-interaction entry point
+    assert np.abs(mb.forces(s) - f).max() < 1e-9 and abs(mb.potential_energy(s) - e) < 1e-9 * abs(e)
+    # bonded-only parity: pairwise-only seam (mb_forces) subtracted
+    f_pair = _pairwise_forces(s)
     fb_ref = sum(g[f"forces_{k}_only"] for k in ("bond", "angle", "proptor", "improptor"))
     assert np.linalg.norm((f - f_pair) - fb_ref, axis=1).max() < 1e-7
     s.close()
@@ -298,7 +312,7 @@ def test_6mrr_all_cut_f32_vs_oracle(golden_6mrr):
     f_ref, _, _ = orc.forces_allpairs(x32.astype(np.float64), energy=False)
     fb, eb = H.bonded_forces_oracle(g, x32.astype(np.float64))
     f, e = mb.forces_energy(s)
-    fb_gpu = f - mb.forces(s)
+    fb_gpu = f - _pairwise_forces(s)
     berr = np.abs(fb_gpu - fb).max()
     print(f"[6mrr bonded f32] max|dF_bonded|={berr:.3e} (max|F_bonded|={np.abs(fb).max():.3e})")
     assert berr < 1e-4 * np.abs(fb).max() + 5e-2  # stiff bonds (k ~ 4.6e5): (r - r0) cancellation in f32
@@ -518,4 +532,180 @@ def test_c2_energy_conservation_f32():
     st = s.stats()
     print(f"[C2 NVE] E0={e0:.4f} E1={e1:.4f} drift={(e1 - e0) / sd['n']:.3e} kJ/mol/atom KE={ke:.2f} rebuilds={st['n_rebuilds']}")
     assert abs(e1 - e0) / sd["n"] < 2e-3  # ~0.3 % of kT per atom at 90 K
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size parity against the oracle's neighbour-list path (the configs that carry the bench numbers)
+# ---------------------------------------------------------------------------------------------------
+def _full_size_vs_oracle(cells, label):
+    """Forces + energy of the packed-f32 fast path at full size vs the f64 oracle on the same f32-rounded coordinates.
+    Bar: the repo's f32 tolerance (5e-5 max|F| + 2e-3 kJ/mol/nm per component; pairs within f32 rounding of the cutoff
+    may land on either side and are allowed one F(rc) jump each), energy rel 2e-6."""
+    sd = H.lj_fluid(cells, seed=42, dtype=np.float32)
+    inter = (mb.LennardJones(cutoff=mb.DistanceCutoff(1.2), use_neighbors=True),)
+    o_inters = [o.Inter(o.LJ, o.CUT_DISTANCE, 1.2, use_neighbors=True)]
+    s = H.make_system(sd, inter, np.float32, r_list=1.3)
+    f = mb.forces(s)
+    e = mb.potential_energy(s)
+    st = s.stats()
+    orc = H.make_oracle(sd, o_inters, dtype=np.float64)
+    x64 = sd["coords"].astype(np.float64)
+    nl = orc.neighbor_list(x64, 1.2 * (1 + 3e-6))
+    f_ref, e_ref, _ = orc.forces_nl(x64, nl)
+    fmax = np.abs(f_ref).max()
+    per_atom = np.abs(f.astype(np.float64) - f_ref).max(axis=1)
+    lo = orc.neighbor_list(x64, 1.2 * (1 - 3e-6))
+    on_cut = np.zeros(sd["n"])
+    key = lambda a: a[:, 0].astype(np.int64) * sd["n"] + a[:, 1]
+    extra = nl[~np.isin(key(nl), key(lo))]
+    np.add.at(on_cut, extra[:, 0], 1)
+    np.add.at(on_cut, extra[:, 1], 1)
+    fc = _cutoff_force_bound(sd, o_inters)
+    print(f"[{label}] n={sd['n']} bricks={st['n_bricks']} brick={st['brick_dims']} in-cutoff pairs={len(lo)} "
+          f"max|dF|={per_atom.max():.3e} (max|F|={fmax:.3e}) pairs on the cutoff={len(extra)} F(rc)={fc:.3e} "
+          f"dE/E={(e - e_ref) / abs(e_ref):.3e}")
+    assert (per_atom <= _tol(np.float32, fmax) + on_cut * fc).all()
+    assert abs(e - e_ref) <= _etol(np.float32, e_ref)
+    assert np.array_equal(f, mb.forces(s))
+    return sd, s, orc
+
+
+def test_c2_full_size_vs_oracle():
+    """BASELINE config 2 (256 000 atoms, f32, rc 1.2 nm, brick 3x3x2): single evaluation, then 100 VelocityVerlet steps
+    against the oracle's VV loop (bar: test/simulation.jl:1246-1252, 1e-4 nm for the f32 GPU path)."""
+    sd, s, orc = _full_size_vs_oracle(40, "C2 full size")
+    x_ref, v_ref, _ = orc.simulate_vv(sd["coords"], sd["velocities"], 0.002, 100, remove_cm_every=1, r_list=1.4, nl_every=10)
+    mb.simulate(s, mb.VelocityVerlet(dt=0.002), 100)
+    ex, ev = _pos_err(s.coords, x_ref, sd["box"]), np.abs(s.velocities - v_ref).max()
+    st = s.stats()
+    print(f"[C2 VV 100 steps f32 vs f64 oracle] dx={ex:.3e} nm dv={ev:.3e} nm/ps rebuilds={st['n_rebuilds']} graph={st['graph_mode']}")
+    assert ex < 1e-4
+    s.close()
+
+
+def test_c4_full_size_vs_oracle():
+    """BASELINE config 4 (1 000 188 atoms): single force + energy evaluation vs the oracle."""
+    sd, s, _ = _full_size_vs_oracle(63, "C4 full size")
+    assert sd["n"] == 1000188
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# boundary contract details (SURVEY.md §8 A1, A2)
+# ---------------------------------------------------------------------------------------------------
+def test_forces_add_into_nonzero_fs_mat_and_device_pointers():
+    """pairwise_forces_loop_gpu! ADDs into fs_mat (force.jl:1216 zeroes it first; the kernel contract is +=), for host
+    and for device output arrays; mb_set_atoms accepts a device pointer (what the Julia shim passes: CuArray{Atom})."""
+    import ctypes as C
+    import torch
+    sd = H.lj_fluid(9, seed=42, dtype=np.float64)
+    inter = (mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True),)
+    s = H.make_system(sd, inter, np.float64, r_list=1.2)
+    f0 = mb.forces(s)
+    pre = np.random.default_rng(0).normal(size=f0.shape)
+    fs = pre.copy()
+    mb.capi.check(s._L.mb_forces(s.engine(), s.coords.ctypes.data, fs.ctypes.data, None, 0))
+    assert np.abs(fs - (pre + f0)).max() <= 1e-12 * np.abs(f0).max()
+    # device output + device coords
+    xd = torch.from_numpy(s.coords).cuda()
+    fd = torch.from_numpy(pre).cuda()
+    mb.capi.check(s._L.mb_forces(s.engine(), xd.data_ptr(), fd.data_ptr(), None, 0))
+    torch.cuda.synchronize()
+    assert np.abs(fd.cpu().numpy() - (pre + f0)).max() <= 1e-12 * np.abs(f0).max()
+    # energy ADD
+    pe = np.array([7.5])
+    mb.capi.check(s._L.mb_energy(s.engine(), s.coords.ctypes.data, pe.ctypes.data, 0))
+    assert abs(pe[0] - 7.5 - mb.potential_energy(s)) < 1e-9 * abs(pe[0])
+    # atoms from a device pointer: a second context fed the same AoS bytes from device memory
+    L = s._L
+    ctx = C.c_void_p()
+    mb.capi.check(L.mb_ctx_create(0, 64, None, C.byref(ctx)))
+    atoms_dev = torch.from_numpy(s.atoms.view(np.uint8).copy()).cuda()
+    mb.capi.check(L.mb_set_atoms(ctx, s.n, atoms_dev.data_ptr()))
+    mb.capi.check(L.mb_set_box(ctx, (C.c_double * 3)(*sd["box"])))
+    d = inter[0].descriptor()
+    mb.capi.check(L.mb_set_inters(ctx, 1, (mb.capi.MBInter * 1)(d)))
+    mb.capi.check(L.mb_set_neighbor_policy(ctx, 1.2, 0))
+    f2 = np.zeros_like(f0)
+    mb.capi.check(L.mb_forces(ctx, s.coords.ctypes.data, f2.ctypes.data, None, 0))
+    assert np.array_equal(f2, f0)
+    L.mb_ctx_destroy(ctx)
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# two-point cutoffs (SURVEY.md §8f-4; src/cutoffs.jl:174-253)
+# ---------------------------------------------------------------------------------------------------
+def test_two_point_cutoff_literals_through_abi():
+    """test/interactions.jl:1574-1635: LJ (sigma 0.3, eps 0.2) at r = 0.7 nm, dist_cutoff 0.8, dist_activation 0.6,
+    evaluated by the CUDA kernels; exactly zero beyond the cutoff; unchanged below the activation distance."""
+    lit = [(mb.CubicSplineCutoff(0.6, 0.8), -0.06201171875, -0.00312500000),
+           (mb.PolynomialCutoff(0.6, 0.8), -0.06716652806, -0.00246320097)]
+    for cut, f_ref, e_ref in lit:
+        for dtype, tol in ((np.float64, 1e-9), (np.float32, 2e-7)):
+            atoms = mb.atoms_from_arrays([10, 10], [1.0, 1.0], [0.3, 0.3], [0.2, 0.2], dtype)
+            def pair(r):
+                s = mb.System(atoms=atoms, coords=np.array([[1.0, 1, 1], [1.0 + r, 1, 1]]), boundary=mb.CubicBoundary(5.0),
+                              pairwise_inters=(mb.LennardJones(cutoff=cut),), dtype=dtype)
+                out = mb.forces(s)[1, 0], mb.potential_energy(s)
+                s.close()
+                return out
+            f, e = pair(0.7)
+            assert abs(f - f_ref) < tol and abs(e - e_ref) < tol, (cut, dtype, f, e)
+            f, e = pair(0.85)
+            assert f == 0.0 and e == 0.0
+            f, e = pair(0.5)
+            f0, e0 = -24 * 0.2 / 0.5 * (2 * 0.6 ** 12 - 0.6 ** 6), 4 * 0.2 * (0.6 ** 12 - 0.6 ** 6)  # plain LJ, sigma/r = 0.6
+            assert abs(f + f0) < 50 * tol and abs(e - e0) < 50 * tol
+    with pytest.raises(ValueError):
+        mb.CubicSplineCutoff(0.8, 0.6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("cut", ["cubic_spline", "polynomial"])
+def test_two_point_cutoffs_brick_and_allpairs(dtype, cut):
+    """CubicSpline / Polynomial cutoffs on LJ + Coulomb through both kernels vs the oracle
+    (exercised by the reference in test/simulation.jl:565-572, test/energy_conservation.jl:21-26)."""
+    mcut = {"cubic_spline": mb.CubicSplineCutoff, "polynomial": mb.PolynomialCutoff}[cut](0.8, 1.0)
+    ocut = {"cubic_spline": o.CUT_CUBIC_SPLINE, "polynomial": o.CUT_POLYNOMIAL}[cut]
+    mi = (mb.LennardJones(cutoff=mcut, weight_special=0.5, use_neighbors=True),
+          mb.Coulomb(cutoff=mcut, weight_special=0.8333, use_neighbors=True))
+    oi = [o.Inter(o.LJ, ocut, 1.0, r_act=0.8, weight_special=0.5, use_neighbors=True),
+          o.Inter(o.COULOMB, ocut, 1.0, r_act=0.8, weight_special=0.8333, use_neighbors=True)]
+    sd = H.molecular_system(1000, [5.1, 5.4, 5.8], seed=5)
+    _check(sd, mi, oi, dtype, r_list=1.1, expect_path=1, label=f"molecular brick {cut}")
+    sd = H.molecular_system(150, [3.0, 3.2, 3.4], seed=11)
+    _check(sd, mi, oi, dtype, r_list=1.1, expect_path=0, label=f"molecular all-pairs {cut}")
+    sd = H.lj_fluid(9, seed=42, dtype=np.float64)
+    _check(sd, (mb.LennardJones(cutoff=mcut, use_neighbors=True),), [o.Inter(o.LJ, ocut, 1.0, r_act=0.8, use_neighbors=True)],
+           dtype, r_list=1.1, expect_path=1, label=f"LJ fluid {cut} (uniform)")
+
+
+# ---------------------------------------------------------------------------------------------------
+# step-adjacent pieces (SURVEY.md §8f-2)
+# ---------------------------------------------------------------------------------------------------
+def test_random_velocities_and_kinetic_tensor(golden_6mrr):
+    """random_velocities! on the device: moments as test/basic.jl:53-72 checks them (statistical parity, SURVEY §8c);
+    kinetic energy tensor (src/energy.jl:56-70) against numpy."""
+    g = golden_6mrr
+    atoms = mb.atoms_from_arrays(g["mass"], g["charge"], g["sigma"], g["eps"], np.float64)
+    s = mb.System(atoms=atoms, coords=g["coords"], boundary=mb.CubicBoundary(*g["box"]), velocities=g["velocities_300K"],
+                  pairwise_inters=(mb.LennardJones(cutoff=mb.DistanceCutoff(1.0), use_neighbors=True),),
+                  neighbor_finder=mb.GPUNeighborFinder(dist_cutoff=1.2), dtype=np.float64)
+    K = mb.kinetic_energy_tensor(s)
+    K_ref = 0.5 * np.einsum("i,ia,ib->ab", g["mass"], g["velocities_300K"], g["velocities_300K"])
+    assert np.abs(K - K_ref).max() < 1e-9 * np.abs(K_ref).max()
+    assert abs(np.trace(K) - 65521.87288132431) < 1.5e-8 * 65521.87288132431  # test/protein.jl:284
+    v = mb.random_velocities(s, 300.0, rng=np.random.default_rng(5))
+    sd_ref = np.sqrt(mb.BOLTZMANN_K * 300.0 / g["mass"])
+    z = v / sd_ref[:, None]
+    n = z.size
+    print(f"[random_velocities] mean={z.mean():.4f} var={z.var():.4f} kurt={np.mean(z ** 4):.3f} n={n}")
+    assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n) and abs(np.mean(z ** 4) - 3) < 0.1
+    assert abs(np.corrcoef(z[:, 0], z[:, 1])[0, 1]) < 4 / np.sqrt(len(z))
+    s.velocities[...] = v
+    assert abs(mb.temperature(s) - 300.0) < 6.0
+    v2 = mb.random_velocities(s, 300.0, rng=np.random.default_rng(5))
+    assert np.array_equal(v, v2)  # same rng state -> same stream
     s.close()

@@ -205,6 +205,48 @@ def test_6mrr_all_pme_openmm_golden(golden_6mrr):
     assert abs(e_tot - float(g["energy_all_pme_exact"])) < 1e-5
 
 
+def test_6mrr_all_pme_approx_erfc_openmm_golden(golden_6mrr):
+    """The reference's DEFAULT CoulombEwald (approximate_erfc=true, coulomb.jl:1331, calc_erfc :1384-1393) against
+    OpenMM's non-exact goldens forces_all_pme / energy_all_pme with the reference's tolerances for that case
+    (test/protein.jl:267, :274: 1e-3 kJ/mol/nm, 0.2 kJ/mol)."""
+    from oracle import pme
+    g = golden_6mrr
+    sd = H.sixmrr_description(g)
+    alpha = pme.pme_alpha(1.0)
+    inters = [o.Inter(o.LJ, o.CUT_DISTANCE, 1.0, weight_special=float(g["lj14scale"]), use_neighbors=True),
+              o.Inter(o.EWALD_REAL, o.CUT_DISTANCE, 1.0, weight_special=float(g["coulomb14scale"]), ewald_alpha=alpha,
+                      use_neighbors=True, approx_erfc=True)]
+    orc = H.make_oracle(sd, inters, dtype=np.float64)
+    f, e, _ = orc.forces_allpairs(sd["coords"])
+    fb, eb = H.bonded_forces_oracle(g, sd["coords"])
+    fr, er, _ = pme.pme_reciprocal(sd["coords"], g["charge"], g["box"], r_cut=1.0, error_tol=0.0005, order=5)
+    fx, ex = pme.ewald_exclusion(sd["coords"], g["charge"], g["box"], np.concatenate([g["excluded"], g["special"]]))
+    e_tot = e + eb + er + ex + o.lj_dispersion_correction_energy(g["sigma"], g["eps"], g["box"], 1.0)
+    df = np.linalg.norm(f + fb + fr + fx - g["forces_all_pme"], axis=1).max()
+    de = abs(e_tot - float(g["energy_all_pme"]))
+    print("approx erfc vs all_pme: max|dF| =", df, "dE =", de)
+    assert df < 1e-3 and de < 0.2
+    # (the reference ships byte-identical all_pme / all_pme_exact files: the looser tolerance IS the polynomial's error,
+    # measured here 4.6e-4 kJ/mol/nm and 0.12 kJ/mol; the exact variant must not pass the tight bar by accident)
+    assert df > 1e-7
+
+
+def test_6mrr_vv_100steps_openmm_trajectory(golden_6mrr):
+    """Oracle pin of the WHOLE step loop: 100 VelocityVerlet steps (dt 0.5 fs) of the :pme system from velocities_300K
+    against OpenMM's coordinates_100steps / velocities_100steps with the reference's bars (test/protein.jl:277-299:
+    1e-10 nm, 1e-7 nm/ps)."""
+    g = golden_6mrr
+    sd = H.sixmrr_description(g)
+    x, v = H.oracle_vv_pme(g, sd["coords"], g["velocities_300K"], 0.0005, 100)
+    box = g["box"]
+    x_ref = g["coordinates_100steps"] - np.floor(g["coordinates_100steps"] / box) * box
+    d = x - x_ref
+    d -= box * np.round(d / box)
+    dx, dv = np.linalg.norm(d, axis=1).max(), np.linalg.norm(v - g["velocities_100steps"], axis=1).max()
+    print("oracle VV 100 steps vs OpenMM: dx =", dx, "dv =", dv)
+    assert dx < 1e-10 and dv < 1e-7
+
+
 def test_cutoff_literals_all_six():
     """test/interactions.jl:1574-1635: LJ (sigma 0.3, eps 0.2) at r = 0.7 nm under the six cutoffs (dist_cut 0.8,
     dist_act 0.6), and exactly zero at r = 1.0 / 0.95 nm. CubicSpline / Polynomial exist in the
