@@ -7,10 +7,14 @@
 //   pos4[slot]  = (x, y, z, q)            T4   positions are continuous (unwrapped) between rebuilds
 //   lj2[slot]   = (sigma part, eps part)  T2   Lorentz: sigma/2, sqrt(eps)  (0,0 if LJ zero shortcut)
 //   orig[slot]  = original atom index     int32
-// A brick is a box of b[0] x b[1] x b[2] cells owned by one CTA. Its halo is the brick plus h cells on
-// every side; every (y,z) row of halo cells is at most 3 contiguous slot runs (periodic wrap in x),
-// which is what the force kernel stages into shared memory with 1-D bulk async copies (TMA).
-// Neighbour list entries are 16-bit indices into that staged halo.
+// A brick is a box of b[0] x b[1] x b[2] cells. Its halo is the brick plus h cells on every side.
+// Positions are ALSO kept in an extended (ghost-padded) array pos4e: the cell grid grown by h cells on every side,
+// x-fastest, the ghost cells holding the periodic images (coordinates already moved by +-L). Every (y,z) row of a
+// brick's halo is then ONE contiguous run of pos4e, in the frame of the owned atoms, which the force kernel and the
+// list builder stage into shared memory with 1-D bulk async copies (TMA) - no wrap splitting, no image arithmetic
+// after the copy. The drift kernel (K1) keeps pos4e current: it stores every atom's new position at ext_of[slot] and
+// at its ghost copies (a third of the atoms sit within h cells of a box face and have 1-7 of them).
+// Neighbour list entries are 16-bit offsets into the staged halo.
 //
 // Every kernel of the rebuild pipeline is gated on ctl->rebuild so the whole sequence can be
 // enqueued unconditionally (no host round trip when no atom moved more than skin/2).
@@ -22,15 +26,17 @@ namespace mb {
 struct Control {
     int rebuild;        // gate: rebuild requested (set by the drift/ingest kernels or by the host)
     int disp;           // an atom moved more than skin/2 since the last build (fixed-interval policy)
-    int overflow;       // bit0 halo capacity, bit1 list stride, bit2 special stride
+    int overflow;       // bit0 halo capacity, bit1 list stride, bit2 special stride, bit3 task table, bit4 extended array / ghost table
     int violations;
-    int prune;          // gate: the inner (pruned) lists must be refreshed from the outer lists
-    int n_prunes;
+    int max_icount;     // most atoms any brick owns (sizes the per-brick task table)
+    int n_ghost;        // ghost copies in pos4e (extended array) of the last build
     unsigned long long n_rebuilds;
     unsigned long long n_pairs;  // real full-shell entries of the last build
     int max_neighbors;
     int max_halo;
     int max_special;
+    int n_ext;          // atoms + ghost copies in the extended array of the last build
+    int pad2_;          // (keeps rebuild_every .. call_max_disp2_bits a 48-byte tail the host uploads in one copy)
     unsigned int ticket;  // last-block-done counter
     int rebuild_every;    // fixed-interval policy (0 = displacement-triggered)
     long long step;       // MD step counter (simulate!'s step_n), advanced on the device
@@ -49,7 +55,7 @@ struct BrickHdr {
     int pad[3];
 };
 struct Run {
-    int gstart, count, soff, shift;  // shift packed: (wx+1) | (wy+1)<<2 | (wz+1)<<4
+    int gstart, count, soff, pad;  // gstart: index into the extended array pos4e; soff: index in the staged halo
 };
 struct IRow {
     int slot_begin, count, smem_begin, cum;
@@ -65,12 +71,13 @@ struct Geom {
     int h, H[3];
     int max_runs, hcells, n_irows;
     int halo_cap, stride, sstride;
+    int task_cap;  // entries per brick of the task table (even; 0 while the capacities are being measured)
+    int nce[3], necells, nerows;  // extended grid: nc + 2h cells per dimension, rows = nce[1] * nce[2]
+    int ext_cap, ghost_cap;       // capacities of pos4e / the ghost table (0 while they are being measured)
     int n;        // atoms
     int align;    // atoms per 16 bytes of the lj2 array (2 for float, 1 for double)
     T rlist2;
     T skin_half2;
-    T rinner2;        // dual list: pairs within r_inner at prune time form the list the force kernel walks
-    T skin_in_half2;  // ((r_inner - max r_cut) / 2)^2
 };
 
 __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -147,7 +154,9 @@ __global__ void cell_scan_kernel(const Control* __restrict__ ctl, int ncells, in
         }
         carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (tid == 0) cell_start[ncells] = n;
+    // n >= 0: the caller knows the total; n < 0: the last warp's carry is the total
+    if (n >= 0) { if (tid == 0) cell_start[ncells] = n; }
+    else if (wid == nw - 1 && lane == 0) cell_start[ncells] = carry;
 }
 
 // ---- R3: scatter old slots into their cell segment (order inside the cell fixed up by R4a) -----
@@ -223,12 +232,171 @@ __global__ void permute_commit_kernel(const Control* __restrict__ ctl, int n,
     mass[s] = mass_t[s];
 }
 
+// ---- R4d: extended (ghost-padded) grid ---------------------------------------------------------------------
+// Extended cell (ex, ey, ez), 0 <= e_d < nc_d + 2h, shows primary cell ((e_d - h) mod nc_d); cells outside [h, h + nc_d)
+// are ghosts whose atoms are stored with their coordinates moved by +-L_d. An extended x-row is
+// [last h cells of the primary row | the primary row | its first h cells], so its length and the offset of every cell
+// in it follow from cell_start; only the row starts need a scan (nerows = nce[1] * nce[2] entries).
+template <typename T>
+__device__ __forceinline__ int ext_row_first_cell(const Geom<T>& g, int ey, int ez) {
+    int py = ey - g.h, pz = ez - g.h;
+    py += (py < 0) ? g.nc[1] : 0; py -= (py >= g.nc[1]) ? g.nc[1] : 0;
+    pz += (pz < 0) ? g.nc[2] : 0; pz -= (pz >= g.nc[2]) ? g.nc[2] : 0;
+    return (pz * g.nc[1] + py) * g.nc[0];
+}
+template <typename T>
+__global__ void ext_row_totals_kernel(const Control* __restrict__ ctl, Geom<T> g, const int* __restrict__ cell_start,
+                                      int* __restrict__ erow_total) {
+    if (!ctl->rebuild) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.nerows) return;
+    const int c0 = ext_row_first_cell(g, r % g.nce[1], r / g.nce[1]);
+    const int a = cell_start[c0], b = cell_start[c0 + g.nc[0]];
+    erow_total[r] = (b - a) + (b - cell_start[c0 + g.nc[0] - g.h]) + (cell_start[c0 + g.h] - a);
+}
+template <typename T>
+__global__ void ext_cells_kernel(Control* __restrict__ ctl, Geom<T> g, const int* __restrict__ cell_start,
+                                 const int* __restrict__ erow_start, int* __restrict__ ecell_start) {
+    if (!ctl->rebuild) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > g.necells) return;
+    if (e == g.necells) {
+        const int total = erow_start[g.nerows];
+        ecell_start[e] = total;
+        ctl->n_ext = total;
+        ctl->n_ghost = 0;
+        if (g.ext_cap > 0 && total > g.ext_cap) atomicOr(&ctl->overflow, 16);
+        return;
+    }
+    const int ex = e % g.nce[0], r = e / g.nce[0];
+    const int c0 = ext_row_first_cell(g, r % g.nce[1], r / g.nce[1]);
+    const int a = cell_start[c0], b = cell_start[c0 + g.nc[0]];
+    const int left = b - cell_start[c0 + g.nc[0] - g.h];
+    int off;
+    if (ex < g.h) off = cell_start[c0 + g.nc[0] - g.h + ex] - cell_start[c0 + g.nc[0] - g.h];
+    else if (ex < g.h + g.nc[0]) off = left + cell_start[c0 + ex - g.h] - a;
+    else off = left + (b - a) + cell_start[c0 + ex - g.h - g.nc[0]] - a;
+    ecell_start[e] = erow_start[r] + off;
+}
+
+// Map from slots to the extended array: ext_of[slot] = the atom's own entry; gptr[slot] = first ghost entry | count << 28;
+// ghost table entry = (index in the extended array, image code), code = (sx+1) | (sy+1)<<2 | (sz+1)<<4, s_d in {-1,0,1}.
+template <typename T>
+struct ExtMap {
+    const int* ext_of;
+    const unsigned int* gptr;
+    const int2* ghosts;
+    typename VT<T>::T4* pos4e;
+    double Ld[3];
+};
+template <typename T>
+__device__ __forceinline__ typename VT<T>::T4 image_of(const double Ld[3], typename VT<T>::T4 p, int code) {
+    // +-L in double, one rounding: the staged atom is in the frame of the brick's owned atoms
+    p.x = (T)((double)p.x + (double)((code & 3) - 1) * Ld[0]);
+    p.y = (T)((double)p.y + (double)(((code >> 2) & 3) - 1) * Ld[1]);
+    p.z = (T)((double)p.z + (double)(((code >> 4) & 3) - 1) * Ld[2]);
+    return p;
+}
+// store position p of slot s into an extended array (this rank's or a peer's): the atom's own entry and its ghost copies
+template <typename T>
+__device__ __forceinline__ void ext_store(const ExtMap<T>& m, int s, typename VT<T>::T4 p, typename VT<T>::T4* __restrict__ dst) {
+    dst[m.ext_of[s]] = p;
+    const unsigned int gp = m.gptr[s];
+    const int ng = (int)(gp >> 28);
+    const int2* ge = m.ghosts + (gp & 0x0fffffffu);
+    for (int k = 0; k < ng; k++) {
+        const int2 e = ge[k];
+        dst[e.x] = image_of<T>(m.Ld, p, e.y);
+    }
+}
+// R4e: per-atom extended index + ghost table; also fills pos4e / lj2e for the positions of the rebuild
+template <typename T>
+__global__ void ext_atoms_kernel(Control* __restrict__ ctl, Geom<T> g, const int* __restrict__ cell_start,
+                                 const int* __restrict__ ecell_start, const typename VT<T>::T4* __restrict__ pos4,
+                                 const typename VT<T>::T2* __restrict__ lj2, int* __restrict__ ext_of,
+                                 unsigned int* __restrict__ gptr, int2* __restrict__ ghosts,
+                                 typename VT<T>::T4* __restrict__ pos4e, typename VT<T>::T2* __restrict__ lj2e,
+                                 const int* __restrict__ orig, int* __restrict__ orig_e) {
+    if (!ctl->rebuild) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n) return;
+    if (g.ext_cap <= 0) {  // capacities are being measured: count the ghosts only
+        const typename VT<T>::T4 p = pos4[s];
+        const T x[3] = {p.x, p.y, p.z};
+        int ng = 1;
+        for (int d = 0; d < 3; d++) {
+            const int c = min(max((int)(x[d] * g.inv_cell[d]), 0), g.nc[d] - 1);
+            if (c < g.h || c >= g.nc[d] - g.h) ng *= 2;
+        }
+        if (ng > 1) atomicAdd(&ctl->n_ghost, ng - 1);
+        return;
+    }
+    const typename VT<T>::T4 p = pos4[s];
+    const T x[3] = {p.x, p.y, p.z};
+    int c[3], ne[3], eo[3][2], sh[3][2];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        c[d] = min(max((int)(x[d] * g.inv_cell[d]), 0), g.nc[d] - 1);  // same arithmetic as bin_count_kernel (positions are wrapped)
+        eo[d][0] = c[d] + g.h; sh[d][0] = 0;
+        ne[d] = 1;
+        if (c[d] < g.h) { eo[d][1] = c[d] + g.h + g.nc[d]; sh[d][1] = 1; ne[d] = 2; }           // beyond the high face: +L
+        else if (c[d] >= g.nc[d] - g.h) { eo[d][1] = c[d] + g.h - g.nc[d]; sh[d][1] = -1; ne[d] = 2; }  // below the low face: -L
+    }
+    const int cid = (c[2] * g.nc[1] + c[1]) * g.nc[0] + c[0];
+    const int k = s - cell_start[cid];
+    const int ng = ne[0] * ne[1] * ne[2] - 1;
+    unsigned int base = 0;
+    bool ok = true;
+    if (ng > 0) {
+        base = (unsigned int)atomicAdd(&ctl->n_ghost, ng);
+        if ((int)base + ng > g.ghost_cap) { atomicOr(&ctl->overflow, 16); ok = false; }
+    }
+    const typename VT<T>::T2 lj = lj2 ? lj2[s] : make2<T>((T)0, (T)0);
+    const int oa = orig_e ? orig[s] : 0;
+    int w = 0;
+    for (int iz = 0; iz < ne[2]; iz++)
+        for (int iy = 0; iy < ne[1]; iy++)
+            for (int ix = 0; ix < ne[0]; ix++) {
+                const int e = (eo[2][iz] * g.nce[1] + eo[1][iy]) * g.nce[0] + eo[0][ix];
+                const int ei = ecell_start[e] + k;
+                if (ei >= g.ext_cap) continue;  // (overflow is flagged by ext_cells_kernel)
+                const int code = (sh[0][ix] + 1) | ((sh[1][iy] + 1) << 2) | ((sh[2][iz] + 1) << 4);
+                if (ix + iy + iz == 0) {
+                    ext_of[s] = ei;
+                    pos4e[ei] = p;
+                } else {
+                    if (ok) ghosts[base + w] = make_int2(ei, code);
+                    w++;
+                    pos4e[ei] = image_of<T>(g.Ld, p, code);
+                }
+                if (lj2e) lj2e[ei] = lj;
+                if (orig_e) orig_e[ei] = oa;
+            }
+    gptr[s] = ok ? (base | ((unsigned int)ng << 28)) : 0u;
+}
+// refresh pos4e from pos4 for slots [s0, s0 + n) (after an ingest without a rebuild, or after a halo exchange over NCCL)
+template <typename T>
+__global__ void ext_fill_kernel(ExtMap<T> m, int s0, int n, const typename VT<T>::T4* __restrict__ pos4) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ext_store<T>(m, s0 + k, pos4[s0 + k], m.pos4e);
+}
+
+// Task table: one int2 per owned atom of a brick, [brick * task_cap + task] = (slot, staged index | main-list length << 12 |
+// special-list length << 24). brick_tables_kernel writes (slot, staged index), build_lists_kernel adds the lengths. The
+// force kernel's producer warp copies a brick's entries into shared memory together with the halo.
+constexpr int TASK_MAX_MAIN = 4095, TASK_MAX_SPECIAL = 255;
+__host__ __device__ inline int task_pack(int si, int n_main, int n_spec) { return si | (n_main << 12) | (n_spec << 24); }
+
+
 // ---- R5: brick tables ---------------------------------------------------------------------------
-// One CTA per brick. Outputs: hdr, runs[max_runs], irows[n_irows], hcs[hcells] (start,end per halo cell).
+// One CTA per brick. Outputs: hdr, runs[max_runs] (one per (y,z) row of the halo: a contiguous range of the extended
+// array), irows[n_irows], hcs[hcells] (start,end per halo cell in the staged halo), task table.
 template <typename T>
 __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const int* __restrict__ cell_start,
-                                    BrickHdr* __restrict__ hdrs, Run* __restrict__ runs, IRow* __restrict__ irows,
-                                    ushort2* __restrict__ hcs, int uniform_lj) {
+                                    const int* __restrict__ ecell_start, BrickHdr* __restrict__ hdrs,
+                                    Run* __restrict__ runs, IRow* __restrict__ irows, ushort2* __restrict__ hcs,
+                                    int2* __restrict__ task_tab, int uniform_lj) {
     if (!ctl->rebuild) return;
     extern __shared__ int s_mem[];
     int* s_len = s_mem;                  // max_runs
@@ -240,7 +408,7 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
     int c0[3], e[3], He[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-        c0[d] = B[d] * g.b[d];
+        c0[d] = B[d] * g.b[d];  // = extended coordinate of the halo's first cell (primary c0 - h, shifted by the h ghost cells)
         e[d] = min(g.b[d], g.nc[d] - c0[d]);
         He[d] = e[d] + 2 * g.h;
     }
@@ -248,25 +416,14 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
     const int A = g.align;
     // pass 1: run extents
     for (int r = tid; r < g.max_runs; r += blockDim.x) {
-        int seg = r % 3, rr = r / 3;
-        int ry = rr % g.H[1], rz = rr / g.H[1];
+        const int ry = r % g.H[1], rz = r / g.H[1];
         Run run = {0, 0, 0, 0};
         int len = 0;
         if (ry < He[1] && rz < He[2]) {
-            int gy = c0[1] + ry - g.h, gz = c0[2] + rz - g.h;
-            int wy = floor_div(gy, g.nc[1]), wz = floor_div(gz, g.nc[2]);
-            int cy = gy - wy * g.nc[1], cz = gz - wz * g.nc[2];
-            int wx = seg - 1;
-            int lo = max(c0[0] - g.h, wx * g.nc[0]);
-            int hi = min(c0[0] + e[0] + g.h - 1, (wx + 1) * g.nc[0] - 1);
-            if (lo <= hi) {
-                int cid_lo = (cz * g.nc[1] + cy) * g.nc[0] + (lo - wx * g.nc[0]);
-                int cid_hi = (cz * g.nc[1] + cy) * g.nc[0] + (hi - wx * g.nc[0]);
-                run.gstart = cell_start[cid_lo];
-                run.count = cell_start[cid_hi + 1] - run.gstart;
-                run.shift = (wx + 1) | ((wy + 1) << 2) | ((wz + 1) << 4);
-                if (run.count > 0) len = ((run.gstart % A) + run.count + A - 1) / A * A;
-            }
+            const int e_lo = ((c0[2] + rz) * g.nce[1] + (c0[1] + ry)) * g.nce[0] + c0[0];
+            run.gstart = ecell_start[e_lo];
+            run.count = ecell_start[e_lo + He[0]] - run.gstart;
+            if (run.count > 0) len = ((run.gstart % A) + run.count + A - 1) / A * A;
         }
         my_runs[r] = run;
         s_len[r] = len;
@@ -291,7 +448,6 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
     }
     __syncthreads();
     unsigned int tx_pos = 0, tx_lj = 0;
-    int any_shift = 0;
     for (int r = tid; r < g.max_runs; r += blockDim.x) {
         Run run = my_runs[r];
         if (run.count > 0) {
@@ -299,17 +455,14 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
             my_runs[r].soff = run.soff;
             tx_pos += (unsigned int)run.count * (unsigned int)sizeof(typename VT<T>::T4);
             if (!uniform_lj) tx_lj += (unsigned int)s_len[r] * (unsigned int)sizeof(typename VT<T>::T2);
-            if (run.shift != (1 | (1 << 2) | (1 << 4))) any_shift = 1;
         }
     }
-    // block reduce tx / any_shift through shared atomics
+    // block reduce tx through shared atomics
     __shared__ unsigned int s_tx_pos, s_tx_lj;
-    __shared__ int s_any;
-    if (tid == 0) { s_tx_pos = 0; s_tx_lj = 0; s_any = 0; }
+    if (tid == 0) { s_tx_pos = 0; s_tx_lj = 0; }
     __syncthreads();
     if (tx_pos) atomicAdd(&s_tx_pos, tx_pos);
     if (tx_lj) atomicAdd(&s_tx_lj, tx_lj);
-    if (any_shift) atomicOr(&s_any, 1);
     __syncthreads();
     // halo cell table
     ushort2* my_hcs = hcs + (size_t)b * g.hcells;
@@ -317,12 +470,9 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
         int rx = hc % g.H[0], ry = (hc / g.H[0]) % g.H[1], rz = hc / (g.H[0] * g.H[1]);
         ushort2 se = make_ushort2(0, 0);
         if (rx < He[0] && ry < He[1] && rz < He[2]) {
-            int gx = c0[0] + rx - g.h, gy = c0[1] + ry - g.h, gz = c0[2] + rz - g.h;
-            int wx = floor_div(gx, g.nc[0]), wy = floor_div(gy, g.nc[1]), wz = floor_div(gz, g.nc[2]);
-            int cid = ((gz - wz * g.nc[2]) * g.nc[1] + (gy - wy * g.nc[1])) * g.nc[0] + (gx - wx * g.nc[0]);
-            int r = (rz * g.H[1] + ry) * 3 + (wx + 1);
-            Run run = my_runs[r];
-            int cs = cell_start[cid], ce = cell_start[cid + 1];
+            const int ec = ((c0[2] + rz) * g.nce[1] + (c0[1] + ry)) * g.nce[0] + c0[0] + rx;
+            const Run run = my_runs[rz * g.H[1] + ry];
+            const int cs = ecell_start[ec], ce = ecell_start[ec + 1];
             int st = run.soff + (cs - run.gstart);
             int en = st + (ce - cs);
             st = min(st, 65535);
@@ -332,8 +482,9 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
         my_hcs[hc] = se;
     }
     __syncthreads();
+    __shared__ int s_icount;
+    IRow* my_rows = irows + (size_t)b * g.n_irows;
     if (tid == 0) {
-        IRow* my_rows = irows + (size_t)b * g.n_irows;
         int cum = 0;
         for (int q = 0; q < g.n_irows; q++) {
             int iy = q % g.b[1], iz = q / g.b[1];
@@ -350,111 +501,60 @@ __global__ void brick_tables_kernel(Control* __restrict__ ctl, Geom<T> g, const 
         }
         BrickHdr hd;
         hd.halo_count = s_total;
-        hd.i_count = cum;
+        hd.i_count = (g.ext_cap > 0 && ecell_start[g.necells] > g.ext_cap) ? 0 : cum;  // extended array overflow: nothing may be staged
         hd.tx_pos = s_tx_pos;
         hd.tx_lj = s_tx_lj;
-        hd.any_shift = s_any;
+        hd.any_shift = 0;
         hd.pad[0] = hd.pad[1] = hd.pad[2] = 0;
         hdrs[b] = hd;
+        s_icount = cum;
         atomicMax(&ctl->max_halo, s_total);
+        atomicMax(&ctl->max_icount, cum);
         if (s_total > g.halo_cap) atomicOr(&ctl->overflow, 1);
+        if (g.task_cap > 0 && cum > g.task_cap) atomicOr(&ctl->overflow, 8);
+    }
+    __syncthreads();
+    // task table: (slot, staged index) of every owned atom, rows in order (the list builder adds the list lengths)
+    if (task_tab != nullptr && g.task_cap > 0) {
+        const int nt = min(s_icount, g.task_cap);
+        for (int t = tid; t < nt; t += blockDim.x) {
+            int q = 0;
+            while (q + 1 < g.n_irows && my_rows[q + 1].cum <= t) q++;
+            const IRow row = my_rows[q];
+            task_tab[(size_t)b * g.task_cap + t] = make_int2(row.slot_begin + (t - row.cum), task_pack(row.smem_begin + (t - row.cum), 0, 0));
+        }
     }
 }
 
-// ---- halo staging shared by the list builder and the force kernel -------------------------------
-// Stages pos4 (and optionally lj2) runs of brick b into shared memory with bulk async copies, then
-// converts the positions to the brick-local frame (origin = brick corner, periodic image applied) in
-// double so that i-j differences carry no box-size rounding error.
-// Phase 1: arm the mbarrier and issue the bulk copies (returns right after the issue; the copies are in flight).
-template <typename T, bool WITH_LJ>
-__device__ __forceinline__ void stage_halo_issue(const Geom<T>& g, const BrickHdr& hd, const Run* __restrict__ my_runs,
-                                                 const typename VT<T>::T4* __restrict__ pos4,
-                                                 const typename VT<T>::T2* __restrict__ lj2, typename VT<T>::T4* s_pos,
-                                                 typename VT<T>::T2* s_lj, uint64_t* bar) {
+// ---- halo staging of the list builder (the force kernel's producer warp has its own pipelined copy loop) ---------
+// Stages the pos4e runs of brick b into shared memory with bulk async copies and waits for them. The staged atoms are
+// already in one frame (ghost cells hold shifted images), so nothing is touched after the copy.
+template <typename T>
+__device__ __forceinline__ void stage_halo(const Geom<T>& g, const BrickHdr& hd, const Run* __restrict__ my_runs,
+                                           const typename VT<T>::T4* __restrict__ pos4e, typename VT<T>::T4* s_pos,
+                                           uint64_t* bar) {
     using T4 = typename VT<T>::T4;
-    using T2 = typename VT<T>::T2;
     const int tid = threadIdx.x;
-    const int A = g.align;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
     }
-    if (tid < A) {
-        s_pos[tid] = make4<T>((T)1.0e6, (T)1.0e6, (T)1.0e6, (T)0);  // dummy atom: far away, no charge
-        if (WITH_LJ) s_lj[tid] = make2<T>((T)0, (T)0);
-    }
+    if (tid < g.align) s_pos[tid] = make4<T>((T)1.0e6, (T)1.0e6, (T)1.0e6, (T)0);  // dummy atom: far away, no charge
     __syncthreads();
-    if (tid == 0) mbar_arrive_expect_tx(bar, hd.tx_pos + (WITH_LJ ? hd.tx_lj : 0u));
+    if (tid == 0) mbar_arrive_expect_tx(bar, hd.tx_pos);
     __syncthreads();
     for (int r = tid; r < g.max_runs; r += blockDim.x) {
         Run run = my_runs[r];
-        if (run.count > 0) {
-            bulk_g2s(&s_pos[run.soff], &pos4[run.gstart], (uint32_t)run.count * (uint32_t)sizeof(T4), bar);
-            if (WITH_LJ) {
-                int mis = run.gstart % A;
-                int len = (mis + run.count + A - 1) / A * A;
-                bulk_g2s(&s_lj[run.soff - mis], &lj2[run.gstart - mis], (uint32_t)len * (uint32_t)sizeof(T2), bar);
-            }
-        }
+        if (run.count > 0) bulk_g2s(&s_pos[run.soff], &pos4e[run.gstart], (uint32_t)run.count * (uint32_t)sizeof(T4), bar);
     }
-}
-// Phase 2: wait for the copies, then re-centre bricks that hold periodic images.
-template <typename T, bool ALWAYS_LOCALIZE>
-__device__ __forceinline__ void stage_halo_wait(const Geom<T>& g, int b, const BrickHdr& hd, const Run* __restrict__ my_runs,
-                                                typename VT<T>::T4* s_pos, uint64_t* bar) {
-    using T4 = typename VT<T>::T4;
-    const int tid = threadIdx.x;
     mbar_wait(bar, 0);
-    // Bricks whose halo holds no periodic image keep global coordinates: the pair loop only uses differences of
-    // positions, which are exact in the same frame. Only bricks at the box boundary are re-centred.
-    if (!ALWAYS_LOCALIZE && !hd.any_shift) {
-        __syncthreads();
-        return;
-    }
-    // The list builder works in a brick-local frame (ALWAYS_LOCALIZE: origin = brick corner, its row trimming needs
-    // coordinates relative to the brick). The force kernel only needs every staged atom in the SAME frame as the owned
-    // atoms, so it keeps global coordinates and moves just the runs that are periodic images by +-L (in double, one
-    // rounding) - a fifth of a boundary brick's halo instead of all of it.
-    double org[3] = {0.0, 0.0, 0.0};
-    if (ALWAYS_LOCALIZE) {
-        int B[3] = {b % g.nb[0], (b / g.nb[0]) % g.nb[1], b / (g.nb[0] * g.nb[1])};
-#pragma unroll
-        for (int d = 0; d < 3; d++) org[d] = (double)(B[d] * g.b[d]) * g.celld[d];
-    }
-    constexpr int NO_SHIFT = 1 | (1 << 2) | (1 << 4);
-    // 8-lane groups, one run each (a run is ~40 atoms): four runs per warp instruction
-    const int l8 = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
-    for (int r = grp; r < g.max_runs; r += ngrp) {
-        Run run = my_runs[r];
-        if (run.count <= 0) continue;
-        if (!ALWAYS_LOCALIZE && run.shift == NO_SHIFT) continue;
-        const double ox = (double)((run.shift & 3) - 1) * g.Ld[0] - org[0];
-        const double oy = (double)(((run.shift >> 2) & 3) - 1) * g.Ld[1] - org[1];
-        const double oz = (double)(((run.shift >> 4) & 3) - 1) * g.Ld[2] - org[2];
-        for (int k = l8; k < run.count; k += 8) {
-            T4 p = s_pos[run.soff + k];
-            p.x = (T)((double)p.x + ox);
-            p.y = (T)((double)p.y + oy);
-            p.z = (T)((double)p.z + oz);
-            s_pos[run.soff + k] = p;
-        }
-    }
     __syncthreads();
-}
-template <typename T, bool WITH_LJ, bool ALWAYS_LOCALIZE>
-__device__ __forceinline__ void stage_halo(const Geom<T>& g, int b, const BrickHdr& hd, const Run* __restrict__ my_runs,
-                                           const typename VT<T>::T4* __restrict__ pos4,
-                                           const typename VT<T>::T2* __restrict__ lj2,
-                                           typename VT<T>::T4* s_pos, typename VT<T>::T2* s_lj, uint64_t* bar) {
-    stage_halo_issue<T, WITH_LJ>(g, hd, my_runs, pos4, lj2, s_pos, s_lj, bar);
-    stage_halo_wait<T, ALWAYS_LOCALIZE>(g, b, hd, my_runs, s_pos, bar);
 }
 
 // Main-list entries are stored as halo index << LIST_SHIFT (= byte offset of a float4 position in shared memory): the
 // force kernel saves a shift per entry. 16-bit entries therefore address at most LIST_MAX_HALO staged atoms per brick.
 constexpr int LIST_SHIFT = 4;
 constexpr int LIST_MAX_HALO = 65536 >> LIST_SHIFT;
-
 // ---- R6: full-shell neighbour lists --------------------------------------------------------------
 // One CTA per brick, one warp per owned atom. Entries are 16-bit halo indices written in the lane-
 // swizzled order the force kernel reads (see force.cuh). Excluded pairs are dropped here; special
@@ -463,10 +563,11 @@ template <typename T, bool COUNT_ONLY, bool HAS_EX>
 __global__ void __launch_bounds__(256)
     build_lists_kernel(Control* __restrict__ ctl, Geom<T> g, const BrickHdr* __restrict__ hdrs,
                        const Run* __restrict__ runs, const IRow* __restrict__ irows, const ushort2* __restrict__ hcs,
-                       const typename VT<T>::T4* __restrict__ pos4, const int* __restrict__ orig,
+                       const typename VT<T>::T4* __restrict__ pos4e, const int* __restrict__ orig_e,
                        const int* __restrict__ ex_ptr, const int* __restrict__ ex_idx, const int* __restrict__ sp_ptr,
                        const int* __restrict__ sp_idx, unsigned short* __restrict__ list,
-                       unsigned short* __restrict__ slist, ushort2* __restrict__ counts, int brick0) {
+                       unsigned short* __restrict__ slist, ushort2* __restrict__ counts, int2* __restrict__ task_tab,
+                       int brick0) {
     if (!ctl->rebuild) return;
     using T4 = typename VT<T>::T4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -489,12 +590,21 @@ __global__ void __launch_bounds__(256)
     for (int k = tid; k < g.n_irows; k += blockDim.x) s_rows[k] = irows[(size_t)b * g.n_irows + k];
     __syncthreads();
     fence_proxy_async();
-    stage_halo<T, false, true>(g, b, hd, my_runs, pos4, nullptr, s_pos, nullptr, &s_bar);
-    for (int r = wid; r < g.max_runs; r += nw) {
-        Run run = my_runs[r];
-        for (int k = lane; k < run.count; k += 32) s_orig[run.soff + k] = orig[run.gstart + k];
+    stage_halo<T>(g, hd, my_runs, pos4e, s_pos, &s_bar);
+    if (HAS_EX) {
+        for (int r = wid; r < g.max_runs; r += nw) {
+            Run run = my_runs[r];
+            for (int k = lane; k < run.count; k += 32) s_orig[run.soff + k] = orig_e[run.gstart + k];
+        }
     }
     __syncthreads();
+    // brick corner (the row trimming below works in coordinates relative to it; distances are frame-independent)
+    double org[3];
+    {
+        const int B[3] = {b % g.nb[0], (b / g.nb[0]) % g.nb[1], b / (g.nb[0] * g.nb[1])};
+#pragma unroll
+        for (int d = 0; d < 3; d++) org[d] = (double)(B[d] * g.b[d]) * g.celld[d];
+    }
 
     int my_max = 0;
     unsigned long long my_pairs = 0;
@@ -513,8 +623,9 @@ __global__ void __launch_bounds__(256)
             int hc0 = ((iz + g.h) * g.H[1] + (iy + g.h)) * g.H[0] + g.h;
             while (ix + 1 < g.b[0] && si >= (int)s_hcs[hc0 + ix].y) ix++;
         }
-        T4 pi = s_pos[si];
-        int oi = s_orig[si];
+        const T4 pi = s_pos[si];
+        const T lx = (T)((double)pi.x - org[0]), ly = (T)((double)pi.y - org[1]), lz = (T)((double)pi.z - org[2]);
+        int oi = HAS_EX ? s_orig[si] : 0;
         // exclusion / special partner lists of atom oi into lanes
         int ex_a = ex_ptr ? ex_ptr[oi] : 0, ex_n = ex_ptr ? ex_ptr[oi + 1] - ex_a : 0;
         int sp_a = sp_ptr ? sp_ptr[oi] : 0, sp_n = sp_ptr ? sp_ptr[oi + 1] - sp_a : 0;
@@ -538,14 +649,14 @@ __global__ void __launch_bounds__(256)
             if (r < nrows) {
                 const int rz = iz + r / side, ry = iy + r % side;
                 const T zlo = (T)(rz - g.h) * czv;
-                const T dzm = fmax(fmax(zlo - pi.z, pi.z - (zlo + czv)), (T)0);
+                const T dzm = fmax(fmax(zlo - lz, lz - (zlo + czv)), (T)0);
                 const T ylo = (T)(ry - g.h) * cyv;
-                const T dym = fmax(fmax(ylo - pi.y, pi.y - (ylo + cyv)), (T)0);
+                const T dym = fmax(fmax(ylo - ly, ly - (ylo + cyv)), (T)0);
                 const T rem = rl2 - dym * dym - dzm * dzm;
                 if (rem >= (T)0) {
                     const T wx = fsqrt(rem) + (T)1e-4;
-                    int rx_lo = (int)ffloor((pi.x - wx) * inv_cx) + g.h;
-                    int rx_hi = (int)ffloor((pi.x + wx) * inv_cx) + g.h;
+                    int rx_lo = (int)ffloor((lx - wx) * inv_cx) + g.h;
+                    int rx_hi = (int)ffloor((lx + wx) * inv_cx) + g.h;
                     rx_lo = max(rx_lo, ix);
                     rx_hi = min(rx_hi, ix + 2 * g.h);
                     const int hcrow = (rz * g.H[1] + ry) * g.H[0];
@@ -628,6 +739,8 @@ __global__ void __launch_bounds__(256)
             }
             if (lane == 0) {
                 counts[slot] = make_ushort2((unsigned short)min(count, g.stride), (unsigned short)min(scount, g.sstride));
+                if (task < g.task_cap)
+                    task_tab[(size_t)b * g.task_cap + task] = make_int2(slot, task_pack(si, min(count, g.stride), min(scount, g.sstride)));
                 if (count > g.stride) atomicOr(&ctl->overflow, 2);
                 if (scount > g.sstride) atomicOr(&ctl->overflow, 4);
             }
@@ -651,84 +764,11 @@ __global__ void rebuild_finish_kernel(Control* ctl) {
         if (ctl->disp) ctl->violations++;
         ctl->disp = 0;
         ctl->rebuild = 0;
-        ctl->prune = 1;  // fresh outer lists: derive the inner lists from them
         ctl->n_rebuilds++;
         if (ctl->max_disp2_bits > ctl->call_max_disp2_bits) ctl->call_max_disp2_bits = ctl->max_disp2_bits;
         ctl->max_disp2_bits = 0;
     }
 }
-// ---- dual-list pruning -------------------------------------------------------------------------------
-// The lists built above hold every pair within r_list (outer radius). The force kernel walks a shorter inner
-// list: the pairs within r_inner = max r_cut + inner skin at the last prune, refreshed whenever an atom moved more
-// than half the inner skin (cheap: no cell search, the outer list is the candidate set). Same 16-bit halo indices,
-// same lane-swizzled layout, order preserved. One CTA per brick, 8 lanes per owned atom.
-template <typename T>
-__global__ void __launch_bounds__(256)
-    prune_lists_kernel(const Control* __restrict__ ctl, Geom<T> g, const BrickHdr* __restrict__ hdrs, const Run* __restrict__ runs,
-                       const IRow* __restrict__ irows, const typename VT<T>::T4* __restrict__ pos4,
-                       const unsigned short* __restrict__ olist, const ushort2* __restrict__ ocounts,
-                       unsigned short* __restrict__ ilist, ushort2* __restrict__ icounts,
-                       typename VT<T>::T4* __restrict__ xprune4, int brick0) {
-    if (!ctl->prune) return;
-    using T4 = typename VT<T>::T4;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = blockIdx.x + brick0;
-    const BrickHdr hd = hdrs[b];
-    if (hd.i_count == 0 || hd.halo_count > g.halo_cap) return;
-    T4* s_pos = reinterpret_cast<T4*>(smem_raw);
-    __shared__ uint64_t s_bar;
-    __shared__ IRow s_rows[64];
-    const int tid = threadIdx.x;
-    const Run* my_runs = runs + (size_t)b * g.max_runs;
-    for (int k = tid; k < g.n_irows; k += blockDim.x) s_rows[k] = irows[(size_t)b * g.n_irows + k];
-    stage_halo<T, false, false>(g, b, hd, my_runs, pos4, nullptr, s_pos, nullptr, &s_bar);
-    const int sub = tid >> 3, l = tid & 7;
-    const unsigned int sub_mask = 0xffu << (8 * (sub & 3));
-    const unsigned int lt = (1u << l) - 1u;
-    for (int task = sub; task < hd.i_count; task += 32) {
-        int q = 0;
-        while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
-        const IRow row = s_rows[q];
-        const int slot = row.slot_begin + (task - row.cum);
-        const int si = row.smem_begin + (task - row.cum);
-        const T4 pi = s_pos[si];
-        const ushort2 cnt = ocounts[slot];
-        const int n_groups = ((int)cnt.x + 31) >> 5;
-        const unsigned short* lp = olist + (size_t)slot * g.stride;
-        unsigned short* op = ilist + (size_t)slot * g.stride;
-        int out = 0;
-        for (int gi = 0; gi < n_groups; gi++) {
-            const uint2 w = reinterpret_cast<const uint2*>(lp + gi * 32)[l];
-            const int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
-#pragma unroll
-            for (int e = 0; e < 4; e++) {  // logical entry index inside the group = l + 8 e
-                const T4 pj = s_pos[j[e] >> LIST_SHIFT];
-                const T dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                const bool in = (dx * dx + dy * dy + dz * dz) <= g.rinner2;
-                const unsigned int bal = (__ballot_sync(sub_mask, in) >> (8 * (sub & 3))) & 0xffu;
-                if (in) {
-                    const int m = out + __popc(bal & lt);
-                    op[(m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3)] = (unsigned short)j[e];
-                }
-                out += __popc(bal);
-            }
-        }
-        const int padded = (out + 31) & ~31;
-        for (int m = out + l; m < padded; m += 8) op[(m & ~31) + ((m & 7) << 2) + ((m & 31) >> 3)] = 0;
-        if (l == 0) {
-            icounts[slot] = make_ushort2((unsigned short)out, cnt.y);
-            xprune4[slot] = pos4[slot];
-        }
-    }
-}
-__global__ void prune_finish_kernel(Control* ctl) {
-    if (!ctl->prune) return;
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        ctl->prune = 0;
-        ctl->n_prunes++;
-    }
-}
-
 __global__ void rebuild_begin_kernel(Control* ctl) {
     if (!ctl->rebuild) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -736,6 +776,7 @@ __global__ void rebuild_begin_kernel(Control* ctl) {
         ctl->max_neighbors = 0;
         ctl->max_halo = 0;
         ctl->max_special = 0;
+        ctl->max_icount = 0;
     }
 }
 

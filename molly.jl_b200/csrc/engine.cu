@@ -334,6 +334,8 @@ class Engine : public EngineBase {
         prof_.stream = stream_;
         const char* ng = getenv("MOLLYB200_NO_GRAPH");
         graph_enabled_ = !(ng && ng[0] == '1');
+        const char* ss = getenv("MOLLYB200_STATIC_SCHED");
+        static_sched_ = ss && ss[0] == '1';
     }
     ~Engine() override {
         destroy_graph();
@@ -656,20 +658,6 @@ class Engine : public EngineBase {
         g.ncells = g.nc[0] * g.nc[1] * g.nc[2];
         g.rlist2 = (T)(r_list_ * r_list_);
         g.skin_half2 = (T)(0.25 * skin_ * skin_);
-        {
-            // dual-list pruning is opt-in (MOLLYB200_DUAL=1): measured on B200 it shortens the force kernel by ~6 % but the
-            // prune passes cost more than that at the C2 / C3 skins (profiles/r01_experiments.md)
-            const char* du = getenv("MOLLYB200_DUAL");
-            const char* fr = getenv("MOLLYB200_INNER_SKIN_FRAC");
-            if (fr) inner_frac_ = std::min(1.0, std::max(0.05, atof(fr)));
-            (void)du;
-            dual_ = false;  // measured and rejected (profiles/r01_experiments.md §2); the path is kept for reference but is no
-                            // longer selectable: it has not been re-validated since list entries became byte offsets
-            const double skin_in = dual_ ? skin_ * inner_frac_ : skin_;
-            const double r_in = dual_ ? max_rc_ + skin_in : r_list_;
-            g.rinner2 = (T)(r_in * r_in);
-            g.skin_in_half2 = dual_ ? (T)(0.25 * skin_in * skin_in) : std::numeric_limits<T>::infinity();
-        }
         const double rho_c = (double)n_ / g.ncells;
         const double bytes_per_atom = sizeof(T4) + (P_.uniform_lj ? 0 : sizeof(T2));
         const double smem_budget = (double)smem_optin_ - 4096;
@@ -678,9 +666,13 @@ class Engine : public EngineBase {
             for (int d = 0; d < 3; d++) best[d] = std::min(user_b_[d], g.nc[d]);
             if (nranks_ > 1) best[2] = 1;
         } else {
-            // cost model in pair-evaluation units: every SM works through ceil(nbricks / n_sm) bricks, a brick
-            // costs (owned atoms x neighbours) + ~0.5 per staged halo atom; a lone CTA per SM hides latency badly.
+            // Cost model in pair-evaluation units. The persistent force kernel keeps two CTAs per SM busy through a ring of
+            // stages (one stage = one brick's halo), so a brick costs its pair work plus a staging share per halo atom and a
+            // fixed hand-over cost; smaller bricks balance better across the 2 x n_sm CTAs (dynamic tickets), larger ones
+            // stage fewer halo atoms per owned atom. The stage must leave room for at least two of them per CTA.
             const double nbrs = 4.18879 * r_list_ * r_list_ * r_list_ * (double)n_ / vol;
+            const double cta_budget = ((double)smem_optin_ + 1024.0) / 2.0 - 3072.0;  // two CTAs share an SM's 228 KB
+            const double slots = 2.0 * sm_count_;
             double best_t = 1e300;
             for (int bx = 1; bx <= 8; bx++)
                 for (int by = 1; by <= bx; by++)
@@ -688,16 +680,14 @@ class Engine : public EngineBase {
                         if (bx > g.nc[0] || by > g.nc[1] || bz > g.nc[2]) continue;
                         if (nranks_ > 1 && bz != 1) continue;  // slabs are whole cell layers
                         double halo = (bx + 4.0) * (by + 4.0) * (bz + 4.0) * rho_c * 1.25 + 64;
-                        double smem = halo * bytes_per_atom;
-                        if (smem > smem_budget || halo * 1.1 + 96 > LIST_MAX_HALO) continue;
-                        double occ = std::min(8.0, std::floor(smem_budget / smem));
-                        // latency hiding improves with resident CTAs (8 warps each): measured shape, saturating at ~6
-                        static const double eff_tab[9] = {0.0, 0.35, 0.55, 0.70, 0.80, 0.88, 0.95, 0.97, 1.0};
-                        double eff = eff_tab[(int)occ];
                         double owned = (double)bx * by * bz * rho_c;
-                        double cost_b = owned * nbrs + 2.0 * halo;
+                        double smem = halo * bytes_per_atom + owned * 1.3 * 8.0 + 256;
+                        if (smem > smem_budget || halo * 1.1 + 96 > LIST_MAX_HALO) continue;
+                        const int stages2 = (int)std::floor(cta_budget / smem);  // ring depth with two CTAs per SM
+                        const double eff = stages2 >= 2 ? 1.0 : (stages2 == 1 ? 0.8 : 0.5);
+                        double cost_b = owned * nbrs + 6.0 * halo + 2000.0;
                         double nbr = std::ceil((double)g.nc[0] / bx) * std::ceil((double)g.nc[1] / by) * std::ceil((double)g.nc[2] / bz);
-                        double t = std::ceil(nbr / sm_count_) * cost_b / eff;
+                        double t = (std::max(nbr / slots, 1.0) + 0.5) * cost_b / eff;  // + half a brick of tail
                         if (t < best_t * 0.999) { best_t = t; best[0] = bx; best[1] = by; best[2] = bz; }
                     }
         }
@@ -707,13 +697,45 @@ class Engine : public EngineBase {
             g.H[d] = g.b[d] + 2 * g.h;
         }
         g.nbricks = g.nb[0] * g.nb[1] * g.nb[2];
-        g.max_runs = 3 * g.H[1] * g.H[2];
+        for (int d = 0; d < 3; d++) g.nce[d] = g.nc[d] + 2 * g.h;
+        g.necells = g.nce[0] * g.nce[1] * g.nce[2];
+        g.nerows = g.nce[1] * g.nce[2];
+        g.max_runs = g.H[1] * g.H[2];
         g.hcells = g.H[0] * g.H[1] * g.H[2];
         g.n_irows = g.b[1] * g.b[2];
         return MB_OK;
     }
 
-    size_t force_smem_bytes() const { return (size_t)g_.halo_cap * (sizeof(T4) + (P_.uniform_lj ? 0 : sizeof(T2))); }
+    ExtMap<T> ext_map() const {
+        ExtMap<T> m;
+        m.ext_of = d_ext_of_.as<int>();
+        m.gptr = d_gptr_.as<unsigned int>();
+        m.ghosts = d_ghosts_.as<int2>();
+        m.pos4e = (path_ == 1) ? d_pos4e_.as<T4>() : nullptr;
+        for (int d = 0; d < 3; d++) m.Ld[d] = box_[d];
+        return m;
+    }
+    // pos4e <- pos4 for slots [s0, s0 + n) (positions changed outside K1 and outside a rebuild)
+    int ext_fill(int s0, int n) {
+        if (n <= 0) return MB_OK;
+        ext_fill_kernel<T><<<(n + 255) / 256, 256, 0, stream_>>>(ext_map(), s0, n, d_pos4_.as<T4>());
+        launches_++;
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
+    size_t force_stage() const { return force_stage_bytes<T>(g_.halo_cap, g_.task_cap, P_.uniform_lj != 0); }
+    // launch shape of the persistent force kernel: ring depth and CTAs per SM from the stage size. Two CTAs per SM when at
+    // least one stage each fits (the f64 variants hold 128 registers per thread: one CTA), up to FORCE_MAX_STAGES stages.
+    void force_shape(int& nbuf, int& ctas_per_sm) const {
+        const size_t stage = force_stage();
+        const size_t sm_total = smem_optin_ + 1024;  // 228 KB per SM, 1 KB reserved per resident CTA
+        const size_t static_bytes = 1024;
+        ctas_per_sm = (sizeof(T) == 8) ? 1 : 2;
+        if (ctas_per_sm == 2 && (sm_total / 2 - 1024 - static_bytes) / stage < 1) ctas_per_sm = 1;
+        const size_t budget = (ctas_per_sm == 2) ? sm_total / 2 - 1024 - static_bytes : smem_optin_ - static_bytes;
+        nbuf = (int)std::min<size_t>(FORCE_MAX_STAGES, std::max<size_t>(1, budget / stage));
+        if (const char* e = getenv("MOLLYB200_NBUF")) nbuf = std::max(1, std::min(nbuf, atoi(e)));  // tuning aid: shallower ring
+    }
     size_t build_smem_bytes() const {
         return (size_t)g_.halo_cap * (sizeof(T4) + sizeof(int)) + (size_t)((g_.hcells + 3) & ~3) * sizeof(ushort2) +
                (size_t)g_.n_irows * sizeof(IRow);
@@ -727,6 +749,12 @@ class Engine : public EngineBase {
         MB_CUDA(d_cell_start_.ensure((size_t)(g.ncells + 2) * sizeof(int)));
         MB_CUDA(d_cell_fill_.ensure((size_t)(g.ncells + 2) * sizeof(int)));
         MB_CUDA(cudaMemsetAsync(d_cell_count_.p, 0, (size_t)(g.ncells + 2) * sizeof(int), stream_));
+        MB_CUDA(d_erow_total_.ensure((size_t)(g.nerows + 2) * sizeof(int)));
+        MB_CUDA(d_erow_start_.ensure((size_t)(g.nerows + 2) * sizeof(int)));
+        MB_CUDA(d_erow_fill_.ensure((size_t)(g.nerows + 2) * sizeof(int)));
+        MB_CUDA(d_ecell_start_.ensure((size_t)(g.necells + 2) * sizeof(int)));
+        MB_CUDA(d_ext_of_.ensure((size_t)(n_ + 16) * sizeof(int)));
+        MB_CUDA(d_gptr_.ensure((size_t)(n_ + 16) * sizeof(unsigned int)));
         MB_CUDA(d_hdrs_.ensure((size_t)g.nbricks * sizeof(BrickHdr)));
         MB_CUDA(d_runs_.ensure((size_t)g.nbricks * g.max_runs * sizeof(Run)));
         MB_CUDA(d_irows_.ensure((size_t)g.nbricks * g.n_irows * sizeof(IRow)));
@@ -738,7 +766,11 @@ class Engine : public EngineBase {
         MB_CUDA(d_lj2_t_.ensure(np * sizeof(T2)));
         MB_CUDA(d_orig_t_.ensure(np * sizeof(int)));
         MB_CUDA(d_mass_t_.ensure(np * sizeof(T)));
-        MB_CUDA(d_pe_partial_.ensure((size_t)std::max(g.nbricks, 1) * 7 * sizeof(double)));
+        MB_CUDA(d_pe_partial_.ensure((size_t)std::max(std::max(g.nbricks, 4 * sm_count_), 1) * 7 * sizeof(double)));
+        if (!d_sched_.p) {
+            MB_CUDA(d_sched_.ensure(4 * sizeof(unsigned int)));
+            MB_CUDA(cudaMemsetAsync(d_sched_.p, 0, 4 * sizeof(unsigned int), stream_));
+        }
         return MB_OK;
     }
 
@@ -1007,6 +1039,7 @@ class Engine : public EngineBase {
         for (auto& sg : halo_recv_)
             if (sg.count > 0) MB_NCCL(g_nccl.Recv(d_pos4_.as<T4>() + sg.start, (size_t)sg.count * sizeof(T4), ncclChar, sg.peer, comm_, stream_));
         MB_NCCL(g_nccl.GroupEnd());
+        for (auto& sg : halo_recv_) MB_TRY(ext_fill(sg.start, sg.count));  // received slots -> extended array (+ ghost copies)
         return MB_OK;
     }
     // replicate the owned segments of positions and velocities on every rank (rebuild / export)
@@ -1037,9 +1070,9 @@ class Engine : public EngineBase {
     // by one ncclAllGather, and every rank maps the others'. Any failure on any rank (no peer access, IPC not permitted
     // in this container, too many ranks) leaves ALL ranks on the NCCL transport.
     int p2p_setup() {
-        if (p2p_pos_base_ == d_pos4_.p && !peer_pos_.empty()) return MB_OK;  // mapping is current
+        if (p2p_pos_base_ == d_pos4e_.p && !peer_pos_.empty()) return MB_OK;  // mapping is current
         p2p_close();
-        p2p_pos_base_ = d_pos4_.p;
+        p2p_pos_base_ = d_pos4e_.p;
         peer_pos_.assign(nranks_, nullptr);
         peer_comm_.assign(nranks_, nullptr);
         const char* env = getenv("MOLLYB200_P2P");
@@ -1054,7 +1087,7 @@ class Engine : public EngineBase {
                                 cudaMemcpyHostToDevice, stream_));
         Rec mine;
         memset(&mine, 0, sizeof(mine));
-        if (ok && cudaIpcGetMemHandle(&mine.pos, d_pos4_.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        if (ok && cudaIpcGetMemHandle(&mine.pos, d_pos4e_.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
         if (ok && cudaIpcGetMemHandle(&mine.comm, d_comm_.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
         MB_CUDA(d_ipc_.ensure((size_t)(nranks_ + 1) * sizeof(Rec) + 16));
         Rec* d_all = d_ipc_.as<Rec>();
@@ -1064,7 +1097,7 @@ class Engine : public EngineBase {
         MB_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)nranks_ * sizeof(Rec), cudaMemcpyDeviceToHost, stream_));
         MB_CUDA(cudaStreamSynchronize(stream_));
         for (int r = 0; r < nranks_ && ok; r++) {
-            if (r == rank_) { peer_pos_[r] = d_pos4_.p; peer_comm_[r] = d_comm_.p; continue; }
+            if (r == rank_) { peer_pos_[r] = d_pos4e_.p; peer_comm_[r] = d_comm_.p; continue; }
             if (cudaIpcOpenMemHandle(&peer_pos_[r], all[r].pos, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
                 cudaIpcOpenMemHandle(&peer_comm_[r], all[r].comm, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 ok = 0;
@@ -1184,7 +1217,7 @@ class Engine : public EngineBase {
         const double frac = fr ? atof(fr) : 0.75;
         size_t persist = (size_t)(frac * max_persist);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) != cudaSuccess) { cudaGetLastError(); return MB_OK; }
-        DevBuf& lst = dual_ ? d_ilist_ : d_list_;
+        DevBuf& lst = d_list_;
         size_t bytes = std::min((size_t)n_ * g_.stride * sizeof(unsigned short), (size_t)max_window);
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
@@ -1197,23 +1230,6 @@ class Engine : public EngineBase {
         return MB_OK;
     }
 
-    // gated refresh of the inner lists from the outer lists (dual-list pruning); no-op unless ctl->prune
-    int enqueue_prune() {
-        if (!dual_) return MB_OK;
-        const size_t smem = (size_t)g_.halo_cap * sizeof(T4);
-        MB_CUDA(cudaFuncSetAttribute(prune_lists_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prof_.begin(Prof::REBUILD);
-        prune_lists_kernel<T><<<g_.nbricks, 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
-                                                                d_irows_.as<IRow>(), d_pos4_.as<T4>(), d_list_.as<unsigned short>(),
-                                                                d_counts_.as<ushort2>(), d_ilist_.as<unsigned short>(),
-                                                                d_icounts_.as<ushort2>(), d_xprune4_.as<T4>(), 0);
-        prune_finish_kernel<<<1, 32, 0, stream_>>>(d_ctl_.as<Control>());
-        prof_.end(Prof::REBUILD);
-        launches_ += 2;
-        MB_CUDA(cudaGetLastError());
-        return MB_OK;
-    }
-
     // launch the list builder (count-only or real; with or without exclusion handling)
     int launch_build(bool count_only) {
         const size_t smem = build_smem_bytes();
@@ -1221,11 +1237,12 @@ class Engine : public EngineBase {
         auto go = [&](auto kern) -> int {
             MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<own_nbricks(), 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
-                                                     d_irows_.as<IRow>(), d_hcs_.as<ushort2>(), d_pos4_.as<T4>(), d_orig_.as<int>(),
+                                                     d_irows_.as<IRow>(), d_hcs_.as<ushort2>(), d_pos4e_.as<T4>(), d_orig_e_.as<int>(),
                                                      ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(),
                                                      count_only ? nullptr : d_list_.as<unsigned short>(),
                                                      count_only ? nullptr : d_slist_.as<unsigned short>(),
-                                                     count_only ? nullptr : d_counts_.as<ushort2>(), own_brick0());
+                                                     count_only ? nullptr : d_counts_.as<ushort2>(),
+                                                     count_only ? nullptr : d_task_tab_.as<int2>(), own_brick0());
             return MB_OK;
         };
         if (count_only) { if (has_ex) MB_TRY(go(build_lists_kernel<T, true, true>)); else MB_TRY(go(build_lists_kernel<T, true, false>)); }
@@ -1257,10 +1274,21 @@ class Engine : public EngineBase {
                                                          d_orig_t_.as<int>(), d_mass_t_.as<T>(), d_pos4_.as<T4>(),
                                                          d_vel4_.as<T4>(), d_lj2_.as<T2>(), d_orig_.as<int>(), d_mass_.as<T>(),
                                                          d_xref4_.as<T4>(), d_inv_orig_.as<int>());
+        // extended (ghost-padded) grid: row totals -> row starts (scan) -> cell starts -> per-atom map + ghost copies
+        ext_row_totals_kernel<T><<<(g.nerows + 255) / 256, 256, 0, stream_>>>(ctl, g, d_cell_start_.as<int>(), d_erow_total_.as<int>());
+        cell_scan_kernel<<<1, 1024, 0, stream_>>>(ctl, g.nerows, -1, d_erow_total_.as<int>(), d_erow_start_.as<int>(),
+                                                  d_erow_fill_.as<int>());
+        ext_cells_kernel<T><<<(g.necells + 1 + 255) / 256, 256, 0, stream_>>>(ctl, g, d_cell_start_.as<int>(), d_erow_start_.as<int>(),
+                                                                            d_ecell_start_.as<int>());
+        ext_atoms_kernel<T><<<nb, 256, 0, stream_>>>(ctl, g, d_cell_start_.as<int>(), d_ecell_start_.as<int>(), d_pos4_.as<T4>(),
+                                                     P_.uniform_lj ? nullptr : d_lj2_.as<T2>(), d_ext_of_.as<int>(),
+                                                     d_gptr_.as<unsigned int>(), d_ghosts_.as<int2>(), d_pos4e_.as<T4>(),
+                                                     P_.uniform_lj ? nullptr : d_lj2e_.as<T2>(), d_orig_.as<int>(),
+                                                     (ex_ptr_.empty() && sp_ptr_.empty()) ? nullptr : d_orig_e_.as<int>());
         brick_tables_kernel<T><<<g.nbricks, 128, 2 * g.max_runs * sizeof(int), stream_>>>(
-            ctl, g, d_cell_start_.as<int>(), d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(),
-            d_hcs_.as<ushort2>(), P_.uniform_lj);
-        launches_ += 8;
+            ctl, g, d_cell_start_.as<int>(), d_ecell_start_.as<int>(), d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_irows_.as<IRow>(),
+            d_hcs_.as<ushort2>(), g.task_cap > 0 ? d_task_tab_.as<int2>() : nullptr, P_.uniform_lj);
+        launches_ += 12;
         if (lists) MB_TRY(launch_build(count_only));
         if (!count_only) {
             rebuild_finish_kernel<<<1, 32, 0, stream_>>>(ctl);
@@ -1299,6 +1327,9 @@ class Engine : public EngineBase {
             g_.halo_cap = 65535;
             g_.stride = 0;
             g_.sstride = 0;
+            g_.task_cap = 0;
+            g_.ext_cap = 0;
+            g_.ghost_cap = 0;
             MB_TRY(set_flag_rebuild());
             MB_TRY(enqueue_rebuild(false, true));
             Control c;
@@ -1306,7 +1337,20 @@ class Engine : public EngineBase {
             int cap = (int)(c.max_halo * (1.0 + 0.08 * cap_scale_)) + 32;  // temporal drift of the fullest brick's halo
             cap = (cap + 63) & ~63;
             g_.halo_cap = std::min(cap, LIST_MAX_HALO);
-            size_t need = std::max(force_smem_bytes() + 2048, build_smem_bytes() + 1024);
+            g_.task_cap = (((int)(c.max_icount * (1.0 + 0.08 * cap_scale_)) + 8) + 1) & ~1;  // even: 16-byte rows for the bulk copy
+            MB_CUDA(d_task_tab_.ensure((size_t)g_.nbricks * g_.task_cap * sizeof(int2)));
+            // extended array / ghost table: measured sizes plus room for the boundary cells' population to drift
+            g_.ext_cap = (int)std::min<double>(2.0e9, c.n_ext + (c.n_ext - (double)n_) * 0.10 * cap_scale_ + 1024);
+            g_.ghost_cap = (int)std::min<double>(2.6e8, c.n_ghost * (1.0 + 0.10 * cap_scale_) + 1024);
+            MB_CUDA(d_pos4e_.ensure(((size_t)g_.ext_cap + 64) * sizeof(T4)));
+            MB_CUDA(cudaMemsetAsync(d_pos4e_.p, 0, ((size_t)g_.ext_cap + 64) * sizeof(T4), stream_));
+            if (!P_.uniform_lj) {
+                MB_CUDA(d_lj2e_.ensure(((size_t)g_.ext_cap + 64) * sizeof(T2)));
+                MB_CUDA(cudaMemsetAsync(d_lj2e_.p, 0, ((size_t)g_.ext_cap + 64) * sizeof(T2), stream_));
+            }
+            if (!(ex_ptr_.empty() && sp_ptr_.empty())) MB_CUDA(d_orig_e_.ensure(((size_t)g_.ext_cap + 64) * sizeof(int)));
+            MB_CUDA(d_ghosts_.ensure(((size_t)g_.ghost_cap + 64) * sizeof(int2)));
+            size_t need = std::max(force_stage() + 2048, build_smem_bytes() + 1024);
             if (cap > LIST_MAX_HALO || need > smem_optin_) {  // list entries are 16-bit byte offsets of float4 records
                 // shrink the brick and retry
                 int* ub = user_b_;
@@ -1318,23 +1362,20 @@ class Engine : public EngineBase {
                 for (int d = 0; d < 3; d++) ub[d] = cur[d];
                 continue;
             }
-            // pass B: count neighbours (flag still set because finish did not run)
-            MB_TRY(launch_build(true));
+            // pass B: the pipeline again (idempotent: the positions are sorted) now that the extended array exists, with the
+            // list builder only counting neighbours (the rebuild flag is still set because finish did not run)
+            MB_TRY(enqueue_rebuild(true, true));
             MB_TRY(read_ctl(c));
             int stride = (int)(c.max_neighbors * (1.0 + 0.10 * cap_scale_)) + 16;
             stride = (stride + 31) & ~31;
             g_.stride = std::max(stride, 32);
             g_.sstride = std::max(8, (std::max(c.max_special, max_special_host_) + 7) & ~7);
+            if (g_.stride > TASK_MAX_MAIN || g_.sstride > TASK_MAX_SPECIAL)
+                return set_error(MB_ERR_CAPACITY, "neighbour rows longer than 4095 entries (or more than 255 special partners) are not supported");
             MB_CUDA(d_list_.ensure((size_t)(n_ + 16) * g_.stride * sizeof(unsigned short)));
-            if (dual_) {
-                MB_CUDA(d_ilist_.ensure((size_t)(n_ + 16) * g_.stride * sizeof(unsigned short)));
-                MB_CUDA(d_icounts_.ensure((size_t)(n_ + 16) * sizeof(ushort2)));
-                MB_CUDA(d_xprune4_.ensure((size_t)(n_ + 16) * sizeof(T4)));
-            }
             MB_CUDA(d_slist_.ensure((size_t)(n_ + 16) * g_.sstride * sizeof(unsigned short)));
             // pass C: the real build. The positions are already sorted; the pipeline is idempotent.
             MB_TRY(enqueue_rebuild(true, false));
-            MB_TRY(enqueue_prune());
             MB_TRY(read_ctl(c));
             if (c.overflow) return set_error(MB_ERR_CAPACITY, "neighbour capacity overflow during first build");
             last_ctl_ = c;
@@ -1350,19 +1391,19 @@ class Engine : public EngineBase {
     // ------------------------------------------------------------------------------------------
     template <int COUL, bool UNIFORM, int CUTM, bool ENERGY>
     int launch_force_t(ForceOut<T> out, int brick0, int nbr) {
-        const size_t smem = force_smem_bytes();
-        auto launch = [&](auto kern) -> int {
-            MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            prof_.begin(Prof::FORCE);
-            kern<<<nbr, FORCE_THREADS, smem, stream_>>>(g_, P_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
-                                                               d_irows_.as<IRow>(), d_pos4_.as<T4>(), d_lj2_.as<T2>(),
-                                                               (dual_ ? d_ilist_ : d_list_).template as<unsigned short>(),
-                                                               d_slist_.as<unsigned short>(),
-                                                               (dual_ ? d_icounts_ : d_counts_).template as<ushort2>(), out, brick0);
-            prof_.end(Prof::FORCE);
-            return MB_OK;
-        };
-        MB_TRY(launch(brick_force_kernel<T, COUL, UNIFORM, CUTM, ENERGY, 8>));
+        int nbuf, per_sm;
+        force_shape(nbuf, per_sm);
+        const size_t smem = (size_t)nbuf * force_stage();
+        const int grid = std::max(1, std::min(nbr, per_sm * sm_count_));
+        force_grid_ = grid;
+        auto kern = brick_force_kernel<T, COUL, UNIFORM, CUTM, ENERGY>;
+        MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_.begin(Prof::FORCE);
+        kern<<<grid, FORCE_THREADS, smem, stream_>>>(g_, P_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(), d_task_tab_.as<int2>(),
+                                                     d_pos4e_.as<T4>(), d_lj2e_.as<T2>(), d_list_.as<unsigned short>(),
+                                                     d_slist_.as<unsigned short>(), out, brick0, nbr, nbuf,
+                                                     static_sched_ ? nullptr : d_sched_.as<unsigned int>());
+        prof_.end(Prof::FORCE);
         launches_++;
         n_force_evals_++;
         MB_CUDA(cudaGetLastError());
@@ -1370,8 +1411,12 @@ class Engine : public EngineBase {
     }
     template <int COUL, bool UNIFORM>
     int launch_force_c(bool energy, ForceOut<T> out, int b0, int nbr) {
+#ifdef MB_EXP_FAST  // experiment builds (scripts/): only the plain-cutoff variants are instantiated
+        if (cutm_ != CUTM_PLAIN) return set_error(MB_ERR_INVALID, "experiment build: plain cutoffs only");
+#else
         if (cutm_ == CUTM_TWO_POINT) return energy ? launch_force_t<COUL, UNIFORM, CUTM_TWO_POINT, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, CUTM_TWO_POINT, false>(out, b0, nbr);
         if (cutm_ == CUTM_SHIFTED) return energy ? launch_force_t<COUL, UNIFORM, CUTM_SHIFTED, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, CUTM_SHIFTED, false>(out, b0, nbr);
+#endif
         return energy ? launch_force_t<COUL, UNIFORM, CUTM_PLAIN, true>(out, b0, nbr) : launch_force_t<COUL, UNIFORM, CUTM_PLAIN, false>(out, b0, nbr);
     }
     // owned_only: in a decomposed run the step loop evaluates only this rank's slab of bricks
@@ -1381,15 +1426,19 @@ class Engine : public EngineBase {
         ForceOut<T> out;
         out.f4 = d_f4_.as<T4>();
         out.pe_partial = d_pe_partial_.as<double>();
-        out.vir_partial = d_pe_partial_.as<double>() + g_.nbricks;
+        out.vir_partial = d_pe_partial_.as<double>() + std::max(g_.nbricks, 4 * sm_count_);
         out.gate = gate_;  // one-shot: set by the decomposed step in front of this launch
         memset(&gate_, 0, sizeof(gate_));
         switch (P_.coul_kind) {
             case COUL_NONE:
                 return P_.uniform_lj ? launch_force_c<COUL_NONE, true>(energy, out, b0, nbr) : launch_force_c<COUL_NONE, false>(energy, out, b0, nbr);
+#ifndef MB_EXP_FAST
             case COUL_PLAIN: return launch_force_c<COUL_PLAIN, false>(energy, out, b0, nbr);
-            case COUL_CRF: return launch_force_c<COUL_CRF, false>(energy, out, b0, nbr);
             default: return launch_force_c<COUL_EWALD, false>(energy, out, b0, nbr);
+#else
+            default: return set_error(MB_ERR_INVALID, "experiment build: LJ and LJ + CoulombReactionField only");
+#endif
+            case COUL_CRF: return launch_force_c<COUL_CRF, false>(energy, out, b0, nbr);
         }
     }
 
@@ -1445,12 +1494,12 @@ class Engine : public EngineBase {
                 ingest_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_, coords_dev, vels_dev, d_orig_.as<int>(), d_xref4_.as<T4>(),
                                                           d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->disp);
                 launches_++;
+                MB_TRY(ext_fill(0, (int)n_));
             }
             return MB_OK;
         }
         ingest_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g_, coords_dev, vels_dev, d_orig_.as<int>(), d_xref4_.as<T4>(),
-                                                  d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->rebuild,
-                                                  dual_ ? d_xprune4_.as<T4>() : nullptr, &d_ctl_.as<Control>()->prune);
+                                                  d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->rebuild);
         launches_++;
         if (decomposed()) {
             // every rank holds the full state here; rebuild unconditionally so that ownership is fresh
@@ -1460,7 +1509,7 @@ class Engine : public EngineBase {
             return MB_OK;
         }
         MB_TRY(enqueue_rebuild(true, false));
-        MB_TRY(enqueue_prune());
+        MB_TRY(ext_fill(0, (int)n_));  // (a rebuild refilled pos4e itself; without one the ingested positions go in here)
         return MB_OK;
     }
 
@@ -1500,7 +1549,7 @@ class Engine : public EngineBase {
             if (decomposed()) have_list_ = false;  // forces()/potential_energy() evaluate the whole box on every rank
             MB_TRY(sync_state_from(xc, nullptr));
             MB_TRY(launch_force(energy));
-            n_partials = g_.nbricks;
+            n_partials = force_grid_;
             orig = d_orig_.as<int>();
         }
         if (with_specific) MB_TRY(launch_bonded(pe != nullptr));
@@ -1535,7 +1584,8 @@ class Engine : public EngineBase {
             if ((pe && !pe_dev) || (vir && !vir_dev))
                 MB_CUDA(cudaMemcpyAsync(d_scalars_.p, host_sc, 16 * sizeof(T), cudaMemcpyHostToDevice, stream_));
             double* pp = d_pe_partial_.as<double>();
-            reduce_partials_kernel<T><<<1, 256, 0, stream_>>>(n_partials, pp, pp + n_partials, pe_target, vir_target, nullptr);
+            const double* vp = (path_ == 1) ? pp + std::max(g_.nbricks, 4 * sm_count_) : pp + n_partials;
+            reduce_partials_kernel<T><<<1, 256, 0, stream_>>>(n_partials, pp, vp, pe_target, vir_target, nullptr);
             launches_++;
             if (with_specific && has_specific() && pe_target) {
                 add_double_kernel<T><<<1, 1, 0, stream_>>>(d_sp_energy_.as<double>(), pe_target);
@@ -1573,7 +1623,7 @@ class Engine : public EngineBase {
     };
     int enqueue_step(const StepCfg& c, int do_cm_now, bool clear_cm_after_k1, bool capture,
                      cudaGraphConditionalHandle handle, cudaGraph_t graph, cudaGraph_t* body_out, bool host_rebuild_hint,
-                     cudaGraphConditionalHandle handle_prune = 0, cudaGraph_t* body_prune_out = nullptr, bool defer_cm = false) {
+                     bool defer_cm = false) {
         const bool dec = decomposed() && path_ == 1;
         const int s0 = dec ? own_s0_ : 0, n_own = dec ? own_n_ : (int)n_;
         const int nb = std::max(1, (n_own + 255) / 256);
@@ -1596,8 +1646,7 @@ class Engine : public EngineBase {
         prof_.begin(Prof::VV);
         vv_kick_drift_kernel<T><<<std::min(nb, 4 * sm_count_), 256, 0, stream_>>>(
             s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
-            c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0, (dual_ && path_ == 1) ? d_xprune4_.as<T4>() : nullptr,
-            g_.skin_in_half2, handle_prune, push);
+            c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0, push, ext_map());
         prof_.end(Prof::VV);
         launches_++;
         if (clear_cm_after_k1) {
@@ -1623,17 +1672,6 @@ class Engine : public EngineBase {
             MB_CUDA(cudaGraphAddNode(&cnode, graph, deps, ndeps, &cp));
             *body_out = cp.conditional.phGraph_out[0];
             MB_CUDA(cudaStreamUpdateCaptureDependencies(stream_, &cnode, 1, cudaStreamSetCaptureDependencies));
-            if (dual_) {  // second IF node: refresh the inner lists (after a rebuild, or when the inner skin is used up)
-                cudaGraphNodeParams cq = {cudaGraphNodeTypeConditional};
-                cq.type = cudaGraphNodeTypeConditional;
-                cq.conditional.handle = handle_prune;
-                cq.conditional.type = cudaGraphCondTypeIf;
-                cq.conditional.size = 1;
-                cudaGraphNode_t pnode;
-                MB_CUDA(cudaGraphAddNode(&pnode, graph, &cnode, 1, &cq));
-                *body_prune_out = cq.conditional.phGraph_out[0];
-                MB_CUDA(cudaStreamUpdateCaptureDependencies(stream_, &pnode, 1, cudaStreamSetCaptureDependencies));
-            }
         } else if (dec) {
             if (host_rebuild_hint) {
                 // neighbour rebuild on a decomposed box: replicate positions and velocities, rebuild (identical sort on every
@@ -1648,7 +1686,6 @@ class Engine : public EngineBase {
             }
         } else {
             if (rebuild_every_ == 0 || host_rebuild_hint) MB_TRY(enqueue_rebuild(true, false));
-            MB_TRY(enqueue_prune());
         }
         const int s0b = dec ? own_s0_ : 0, n_ownb = dec ? own_n_ : (int)n_;  // ownership may have changed in the rebuild
         const int nb2 = std::max(1, (n_ownb + 255) / 256);
@@ -1687,12 +1724,12 @@ class Engine : public EngineBase {
     }
 
     struct GraphKey {
-        int path, do_cm, thermostat, geom_version, rebuild_every, dual;
+        int path, do_cm, thermostat, geom_version, rebuild_every;
         double dt, kT, prob;
         int64_t n;
         bool operator==(const GraphKey& o) const {
             return path == o.path && do_cm == o.do_cm && thermostat == o.thermostat && geom_version == o.geom_version &&
-                   rebuild_every == o.rebuild_every && dual == o.dual && dt == o.dt && kT == o.kT && prob == o.prob && n == o.n;
+                   rebuild_every == o.rebuild_every && dt == o.dt && kT == o.kT && prob == o.prob && n == o.n;
         }
     };
     void destroy_graph() {
@@ -1720,15 +1757,13 @@ class Engine : public EngineBase {
             return rc;
         };
         if (cudaGraphCreate(&graph_, 0) != cudaSuccess) return fail(MB_ERR_CUDA);
-        cudaGraphConditionalHandle handle = 0, handle_p = 0;
+        cudaGraphConditionalHandle handle = 0;
         if (path_ == 1 && cudaGraphConditionalHandleCreate(&handle, graph_, 0, cudaGraphCondAssignDefault) != cudaSuccess)
-            return fail(MB_ERR_CUDA);
-        if (path_ == 1 && dual_ && cudaGraphConditionalHandleCreate(&handle_p, graph_, 0, cudaGraphCondAssignDefault) != cudaSuccess)
             return fail(MB_ERR_CUDA);
         if (cudaStreamBeginCaptureToGraph(stream_, graph_, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess)
             return fail(MB_ERR_CUDA);
-        cudaGraph_t body = nullptr, body_p = nullptr;
-        if (enqueue_step(c, c.do_cm, false, true, handle, graph_, &body, false, handle_p, &body_p) != MB_OK) return fail(MB_ERR_CUDA);
+        cudaGraph_t body = nullptr;
+        if (enqueue_step(c, c.do_cm, false, true, handle, graph_, &body, false) != MB_OK) return fail(MB_ERR_CUDA);
         cudaGraph_t out = nullptr;
         if (cudaStreamEndCapture(stream_, &out) != cudaSuccess) return fail(MB_ERR_CUDA);
         const int64_t step_nodes = launches_ - launches_before;
@@ -1738,13 +1773,6 @@ class Engine : public EngineBase {
                 return fail(MB_ERR_CUDA);
             if (enqueue_rebuild(true, false) != MB_OK) return fail(MB_ERR_CUDA);
             if (cudaStreamEndCapture(stream_, &out) != cudaSuccess) return fail(MB_ERR_CUDA);
-            if (dual_) {
-                if (!body_p) return fail(MB_ERR_CUDA);
-                if (cudaStreamBeginCaptureToGraph(stream_, body_p, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess)
-                    return fail(MB_ERR_CUDA);
-                if (enqueue_prune() != MB_OK) return fail(MB_ERR_CUDA);
-                if (cudaStreamEndCapture(stream_, &out) != cudaSuccess) return fail(MB_ERR_CUDA);
-            }
         }
         if (cudaGraphInstantiate(&graph_exec_, graph_, 0) != cudaSuccess) return fail(MB_ERR_CUDA);
         prof_.enabled = prof_was;
@@ -1848,7 +1876,7 @@ class Engine : public EngineBase {
                          !(cm_pending && c.do_cm == 0) && !dec &&  // the decomposed step issues NCCL calls with per-rebuild sizes
                          !pme_on_;                                  // cuFFT launches stay outside the captured step for now
         if (use_graph) {
-            GraphKey key{path_, c.do_cm, c.thermostat ? 1 : 0, geom_version_, rebuild_every_, dual_ ? 1 : 0, p->dt, p->andersen_kT, p->andersen_prob, n_};
+            GraphKey key{path_, c.do_cm, c.thermostat ? 1 : 0, geom_version_, rebuild_every_, p->dt, p->andersen_kT, p->andersen_prob, n_};
             if (!graph_exec_ || !(key == graph_key_)) {
                 if (build_step_graph(c, key) != MB_OK) {
                     graph_failed_ = true;  // stay on the stream path for this context
@@ -1869,7 +1897,7 @@ class Engine : public EngineBase {
                 const bool clear_after_k1 = cm_pending && !do_cm;  // K1 consumed v_cm; nothing overwrites it this step
                 const int every = (dec && rebuild_every_ == 0) ? auto_every_ : rebuild_every_;  // decomposed: fixed interval, adapted per call
                 const bool hint = every > 0 && k > 1 && (step_n - 1) % every == 0;
-                MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint, 0, nullptr, /*defer_cm=*/k < p->n_steps));
+                MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint, /*defer_cm=*/k < p->n_steps));
                 cm_pending = (do_cm != 0) && !c.thermostat;
                 n_steps_++;
             }
@@ -2004,7 +2032,7 @@ class Engine : public EngineBase {
             o->max_neighbors = c.max_neighbors;
             o->max_halo = c.max_halo;
             o->violations = c.violations;
-            o->n_prunes = c.n_prunes;
+            o->n_prunes = 0;
         }
         if (path_ == 1 && have_list_) {
             o->n_list_entries = (int64_t)n_ * g_.stride;
@@ -2082,9 +2110,12 @@ class Engine : public EngineBase {
     DevBuf d_ex_ptr_, d_ex_idx_, d_sp_ptr_, d_sp_idx_;
     DevBuf d_cid_, d_perm_, d_cell_count_, d_cell_start_, d_cell_fill_;
     DevBuf d_hdrs_, d_runs_, d_irows_, d_hcs_, d_counts_, d_list_, d_slist_;
-    DevBuf d_ilist_, d_icounts_, d_xprune4_;  // dual list: inner (pruned) lists + positions at the last prune
-    bool dual_ = false;
-    double max_rc_ = 0, inner_frac_ = 0.4;
+    DevBuf d_erow_total_, d_erow_start_, d_erow_fill_, d_ecell_start_;  // extended (ghost-padded) grid
+    DevBuf d_ext_of_, d_gptr_, d_ghosts_, d_pos4e_, d_lj2e_, d_orig_e_;    // slot -> extended map, ghost table, extended arrays
+    DevBuf d_task_tab_, d_sched_;  // per-brick task tables; brick ticket + finished-CTA counter of the force kernel
+    int force_grid_ = 0;           // CTAs of the last force launch (= number of energy partials)
+    bool static_sched_ = false;    // MOLLYB200_STATIC_SCHED=1: round-robin bricks instead of tickets
+    double max_rc_ = 0;
     DevBuf d_partial_, d_pe_partial_;
 };
 
@@ -2133,7 +2164,11 @@ int mb_ctx_create(int device, int dtype, void* cuda_stream, mb_ctx** out) {
     c->dtype = dtype;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
     if (dtype == 32) c->e.reset(new mb::Engine<float>(device, s));
+#ifndef MB_EXP_FAST
     else c->e.reset(new mb::Engine<double>(device, s));
+#else
+    else { delete c; return mb::set_error(MB_ERR_INVALID, "experiment build: Float32 only"); }
+#endif
     *out = c;
     return MB_OK;
 }

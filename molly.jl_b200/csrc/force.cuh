@@ -1,12 +1,12 @@
 // force.cuh — the non-bonded force/energy kernels.
 //
-// brick_force_kernel: the production path. One CTA per brick of cells; the brick's halo (all atoms
-// within r_list of any owned atom) is staged into shared memory by the TMA engine (cp.async.bulk +
-// mbarrier) as float4 (x,y,z,q) [+ float2 LJ parameters], converted to a brick-local frame, and then
-// every owned atom is processed by LPA (=8) lanes that walk its full-shell neighbour list (16-bit halo
-// indices, read as coalesced 8-byte words) with four independent pair evaluations in flight per lane.
-// Partial forces are reduced with warp shuffles; there are no atomics and no Newton-3 scatter, so
-// results are bitwise reproducible run to run. Replaces force_kernel!/energy_kernel!
+// brick_force_kernel: the production path. Persistent CTAs (two per SM) work through the bricks of cells: a
+// producer warp stages each brick's halo (all atoms within r_list of any owned atom) into a ring of shared-
+// memory stages with the TMA engine (cp.async.bulk + mbarrier) as float4 (x,y,z,q) [+ float2 LJ parameters],
+// periodic images moved into the owned atoms' frame; 15 consumer warps process the owned atoms, 8 lanes per
+// atom walking its full-shell neighbour list (16-bit halo offsets, read as coalesced 8-byte words) with four
+// independent pair evaluations in flight per lane. Partial forces are reduced with warp shuffles; there are no
+// atomics on forces and no Newton-3 scatter, so results are bitwise reproducible run to run. Replaces force_kernel!/energy_kernel!
 // (ext/MollyCUDAExt.jl:1595-2045, :2062-2294) and pairwise_force_kernel_nl! (src/kernels.jl:114-140).
 //
 // allpairs_force_kernel: O(N^2) minimum-image kernel for systems without a usable neighbour list
@@ -19,127 +19,184 @@
 
 namespace mb {
 
-constexpr int FORCE_THREADS = 256;
+// ---- launch shape of the persistent brick kernel ---------------------------------------------------------------
+// 16 warps per CTA: 15 consumer warps evaluate pairs, 1 producer warp feeds them through a ring of up to FORCE_MAX_STAGES
+// shared-memory stages (one stage = one brick's halo + its task table), filled by the TMA engine.
+constexpr int FORCE_THREADS = 512;
+constexpr int FORCE_CONSUMER_WARPS = FORCE_THREADS / 32 - 1;
+constexpr int FORCE_MAX_STAGES = 3;
 #ifndef MB_LIST_BATCH
 #define MB_LIST_BATCH 8
 #endif
 #ifndef MB_USE_F32X2
 #define MB_USE_F32X2 1  // Blackwell packed-f32 (FFMA2/FMUL2) pair loop for the uniform-LJ f32 force path
 #endif
-#ifndef MB_MIN_BLOCKS
-#define MB_MIN_BLOCKS 4
-#endif
 
 template <typename T>
 struct ForceOut {
     typename VT<T>::T4* f4;   // per-slot force (w unused)
-    double* pe_partial;       // [nbricks] (ENERGY)
-    double* vir_partial;      // [nbricks*6] xx,yy,zz,xy,xz,yz (ENERGY)
+    double* pe_partial;       // [gridDim.x] (ENERGY)
+    double* vir_partial;      // [gridDim.x*6] xx,yy,zz,xy,xz,yz (ENERGY)
     PeerWait gate;            // decomposed run over peer memory: epoch flags the halo data of this step arrives under
 };
 
-// f64 variants get half the resident CTAs (128 registers): under the f32 bound of 64 they spilled 560-1113 LDL/STL each
-template <typename T, int COUL, bool UNIFORM, int CUTM, bool ENERGY, int LPA>
-__global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 2 : MB_MIN_BLOCKS)
+struct StageMeta {
+    int brick;    // global brick index staged here
+    int icount;   // owned atoms (tasks) of the brick; -1 = no more work for this CTA
+    int nq;       // quads of 4 tasks
+    int next_q;   // next quad to hand out (force-only launches; energy launches assign quads statically)
+};
+
+// bytes of one stage: positions [+ LJ parameters] of the halo, then the task table
+template <typename T>
+__host__ __device__ inline size_t force_stage_bytes(int halo_cap, int task_cap, bool uniform) {
+    size_t b = (size_t)halo_cap * sizeof(typename VT<T>::T4);
+    if (!uniform) b += (size_t)halo_cap * sizeof(typename VT<T>::T2);
+    b = (b + 127) & ~(size_t)127;
+    b += ((size_t)task_cap * sizeof(int2) + 127) & ~(size_t)127;
+    return b;
+}
+
+// brick_force_kernel — persistent, warp-specialised.
+//   producer warp: takes the next brick (atomic ticket; static round-robin for ENERGY launches so that the per-CTA energy
+//     partials are reproducible), reads its header and run table, issues one bulk async copy (TMA) per (y,z) row of the
+//     halo - a contiguous range of the extended array pos4e, periodic images included - and one for the task table into
+//     the next free stage, and publishes the stage (mbarrier ready[s]) once the bytes have landed. It runs up to
+//     nbuf-1 bricks ahead of the consumers.
+//   consumer warps: take quads (4 consecutive owned atoms, 8 lanes each) of the published stages, walk the four
+//     neighbour rows (software-pipelined: the next quad's first index words are requested while the current one is
+//     evaluated, across stage boundaries), reduce with shuffles and store. A warp releases a stage (mbarrier empty[s])
+//     once it holds no quad in it; there is no CTA-wide barrier in the steady state.
+template <typename T, int COUL, bool UNIFORM, int CUTM, bool ENERGY>
+__global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
     brick_force_kernel(Geom<T> g, PairParams<T> P, const BrickHdr* __restrict__ hdrs, const Run* __restrict__ runs,
-                       const IRow* __restrict__ irows, const typename VT<T>::T4* __restrict__ pos4,
-                       const typename VT<T>::T2* __restrict__ lj2, const unsigned short* __restrict__ list,
-                       const unsigned short* __restrict__ slist, const ushort2* __restrict__ counts, ForceOut<T> out,
-                       int brick0) {
+                       const int2* __restrict__ task_tab, const typename VT<T>::T4* __restrict__ pos4e,
+                       const typename VT<T>::T2* __restrict__ lj2e, const unsigned short* __restrict__ list,
+                       const unsigned short* __restrict__ slist, ForceOut<T> out, int brick0, int nbr, int nbuf,
+                       unsigned int* __restrict__ sched) {
     using T4 = typename VT<T>::T4;
     using T2 = typename VT<T>::T2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = blockIdx.x + brick0;  // brick0: first brick of this rank's slab (0 on a single GPU)
-    const BrickHdr hd = hdrs[b];
-    const int tid = threadIdx.x;
-    if (hd.i_count == 0 || hd.halo_count > g.halo_cap) {
-        if (ENERGY && tid == 0) {
-            out.pe_partial[b] = 0.0;
-            for (int k = 0; k < 6; k++) out.vir_partial[(size_t)b * 6 + k] = 0.0;
+    __shared__ uint64_t s_ready[FORCE_MAX_STAGES], s_empty[FORCE_MAX_STAGES], s_full[FORCE_MAX_STAGES];
+    __shared__ StageMeta s_meta[FORCE_MAX_STAGES];
+    constexpr int NW = FORCE_CONSUMER_WARPS;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const size_t lj_off = (size_t)g.halo_cap * sizeof(T4);
+    const size_t task_off = ((lj_off + (UNIFORM ? 0 : (size_t)g.halo_cap * sizeof(T2))) + 127) & ~(size_t)127;
+    const size_t stage_bytes = force_stage_bytes<T>(g.halo_cap, g.task_cap, UNIFORM);
+    const int A = g.align;
+    if (tid == 0) {
+        for (int s = 0; s < nbuf; s++) {
+            mbar_init(&s_ready[s], 1);
+            mbar_init(&s_empty[s], NW);
+            mbar_init(&s_full[s], 1);
         }
-        return;
+        mbar_fence_init();
+    }
+    if (tid < A * nbuf) {  // dummy atom of every stage (pads of the neighbour rows point at it): far away, no charge, no LJ
+        unsigned char* st = smem_raw + (size_t)(tid / A) * stage_bytes;
+        reinterpret_cast<T4*>(st)[tid % A] = make4<T>((T)1.0e6, (T)1.0e6, (T)1.0e6, (T)0);
+        if (!UNIFORM) reinterpret_cast<T2*>(st + lj_off)[tid % A] = make2<T>((T)0, (T)0);
     }
     if (out.gate.n > 0) {  // the neighbours' drift kernels store this step's halo positions into pos4 (peer.cuh)
         if (tid < out.gate.n) spin_until(out.gate.flag[tid], out.gate.epoch);
-        __syncthreads();
-        fence_proxy_async_all();  // the TMA engine reads them next
     }
-    T4* s_pos = reinterpret_cast<T4*>(smem_raw);
-    T2* s_lj = reinterpret_cast<T2*>(s_pos + g.halo_cap);
-    uint32_t s_pos_u32 = smem_u32(s_pos);
-    asm volatile("" : "+r"(s_pos_u32));  // keep it in a register (otherwise the 5-instruction window-base computation is redone per group)
-    __shared__ uint64_t s_bar;
-    __shared__ IRow s_rows[64];
-    const Run* my_runs = runs + (size_t)b * g.max_runs;
-    for (int k = tid; k < g.n_irows; k += blockDim.x) s_rows[k] = irows[(size_t)b * g.n_irows + k];
-    stage_halo_issue<T, !UNIFORM>(g, hd, my_runs, pos4, lj2, s_pos, s_lj, &s_bar);  // TMA copies in flight from here
+    __syncthreads();
+    if (out.gate.n > 0) fence_proxy_async_all();  // the TMA engine reads them next
 
-    constexpr int NSUB = FORCE_THREADS / LPA;
-    const int sub = tid / LPA, l = tid % LPA;
     T e_acc = (T)0;
     T vir[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
-    // Task bookkeeping. A task = one owned atom handled by one group of LPA lanes. The loop below is software-
-    // pipelined: the list length and the first LIST_HALF index words of task t+1 are requested while task t is being
-    // evaluated, and those of the first task while the halo is still landing, so the global-memory latency of the
-    // neighbour-list stream is off the critical path (each CTA only runs ~4 tasks per lane group).
-    constexpr int LIST_HALF = (MB_LIST_BATCH >= 2) ? MB_LIST_BATCH / 2 : 1;
-    // task -> (slot, shared-memory index): the row search is done once per owned atom into a table instead of once per
-    // lane group and iteration (it was 5 % of the kernel's instructions)
-    constexpr int MAX_TASKS = 512;
-    __shared__ int2 s_task[MAX_TASKS];
-    auto search = [&](int task, int& slot, int& si) {
-        int q = 0;
-        while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
-        const IRow row = s_rows[q];
-        slot = row.slot_begin + (task - row.cum);
-        si = row.smem_begin + (task - row.cum);
-    };
-    const bool tabled = hd.i_count <= MAX_TASKS;
-    if (tabled) {
-        for (int t = tid; t < hd.i_count; t += blockDim.x) {  // s_rows is visible: stage_halo_issue synchronised the CTA
-            int sl, sm;
-            search(t, sl, sm);
-            s_task[t] = make_int2(sl, sm);
-        }
-        __syncthreads();
-    }
-    auto locate = [&](int task, int& slot, int& si) -> bool {
-        const bool valid = task < hd.i_count;
-        slot = 0;
-        si = 0;
-        if (valid) {
-            if (tabled) {
-                const int2 t = s_task[task];
-                slot = t.x;
-                si = t.y;
-            } else {
-                search(task, slot, si);
-            }
-        }
-        return valid;
-    };
-    const int words_in_row = g.stride >> 5;  // groups a row can hold
-    const int n_iter = (hd.i_count + NSUB - 1) / NSUB;
-    int slot, si;
-    bool valid = locate(sub, slot, si);  // s_rows is visible: stage_halo_issue synchronised the CTA
-    ushort2 cnt = valid ? counts[slot] : make_ushort2(0, 0);
-    uint2 wa[LIST_HALF];
-    if (LPA == 8) {
-        const uint2* lp2 = reinterpret_cast<const uint2*>(list + (size_t)slot * g.stride) + l;
-#pragma unroll
-        for (int u = 0; u < LIST_HALF; u++) wa[u] = (valid && u < words_in_row) ? ldg_stream_u2(lp2 + (size_t)u * 8) : make_uint2(0u, 0u);
-    }
-    stage_halo_wait<T, false>(g, b, hd, my_runs, s_pos, &s_bar);
 
-    for (int it = 0; it < n_iter; it++) {
-        const T4 pi = s_pos[si];
-        T lj_s_i = (T)0, lj_e_i = (T)0;
-        if (!UNIFORM) {
-            T2 t = s_lj[si];
-            lj_s_i = t.x;
-            lj_e_i = t.y;
+    if (w == NW) {
+        // =============================== producer warp ===============================
+        int pend = 0, p_s = 0, p_par = 0, p_b = 0, p_icount = 0;  // stage issued but not yet published
+        unsigned int full_bits = 0;  // phase parity of s_full[s] (a stage is only armed when its brick owns atoms)
+        auto publish = [&]() {
+            if (p_icount > 0) mbar_wait(&s_full[p_s], (uint32_t)p_par);  // the stage's bytes have landed
+            __syncwarp();
+            if (lane == 0) {
+                StageMeta mt;
+                mt.brick = p_b;
+                mt.icount = p_icount;
+                mt.nq = (p_icount + 3) >> 2;
+                mt.next_q = 0;
+                s_meta[p_s] = mt;
+                mbar_arrive(&s_ready[p_s]);
+            }
+            pend = 0;
+        };
+        for (int seq = 0;; seq++) {
+            const int s = seq % nbuf, use = seq / nbuf;
+            // (1) next brick: the first one of a CTA is its block index (no ticket latency in front of the first stage), the
+            //     others are drawn from the global ticket counter; static round-robin when the launch asks for it
+            int bi;
+            if (ENERGY || sched == nullptr) {
+                bi = (int)blockIdx.x + seq * (int)gridDim.x;
+            } else if (seq == 0) {
+                bi = (int)blockIdx.x;
+            } else {
+                bi = 0;
+                if (lane == 0) bi = (int)gridDim.x + (int)atomicAdd(sched, 1u);
+                bi = __shfl_sync(0xffffffffu, bi, 0);
+            }
+            const bool last = bi >= nbr;
+            const int c_b = brick0 + (last ? 0 : bi);
+            BrickHdr hd = {0, 0, 0u, 0u, 0, {0, 0, 0}};
+            if (!last) hd = hdrs[c_b];  // in flight while the previous stage lands
+            // (2) publish the stage issued one round earlier. This comes BEFORE waiting for a free stage: a consumer may hold
+            //     stage k while it waits for stage k + nbuf - 1 to be published.
+            if (pend) publish();
+            // (3) a free stage
+            if (use > 0) mbar_wait(&s_empty[s], (uint32_t)((use - 1) & 1));
+            fence_proxy_async();  // generic-proxy accesses of the stage's previous use before the async-proxy writes below
+            if (last) {
+                if (lane == 0) {
+                    StageMeta mt = {0, -1, 0, 0};
+                    s_meta[s] = mt;
+                    mbar_arrive(&s_ready[s]);
+                }
+                break;
+            }
+            // (4) issue the copies
+            const bool skip = hd.i_count == 0 || hd.halo_count > g.halo_cap;
+            const int c_icount = skip ? 0 : min(hd.i_count, g.task_cap);
+            int c_par = 0;
+            if (c_icount > 0) {
+                unsigned char* st = smem_raw + (size_t)s * stage_bytes;
+                T4* sp = reinterpret_cast<T4*>(st);
+                T2* sl = reinterpret_cast<T2*>(st + lj_off);
+                const uint32_t tbytes = ((uint32_t)c_icount * (uint32_t)sizeof(int2) + 15u) & ~15u;
+                c_par = (int)((full_bits >> s) & 1u);
+                full_bits ^= 1u << s;
+                if (lane == 0) mbar_arrive_expect_tx(&s_full[s], hd.tx_pos + (UNIFORM ? 0u : hd.tx_lj) + tbytes);
+                __syncwarp();
+                const Run* my_runs = runs + (size_t)c_b * g.max_runs;
+                for (int r = lane; r < g.max_runs; r += 32) {
+                    const Run run = my_runs[r];
+                    if (run.count > 0) {
+                        bulk_g2s(&sp[run.soff], &pos4e[run.gstart], (uint32_t)run.count * (uint32_t)sizeof(T4), &s_full[s]);
+                        if (!UNIFORM) {
+                            const int mis = run.gstart % A;
+                            const int len = (mis + run.count + A - 1) / A * A;
+                            bulk_g2s(&sl[run.soff - mis], &lj2e[run.gstart - mis], (uint32_t)len * (uint32_t)sizeof(T2), &s_full[s]);
+                        }
+                    }
+                }
+                if (lane == 0) bulk_g2s(st + task_off, task_tab + (size_t)c_b * g.task_cap, tbytes, &s_full[s]);
+            }
+            pend = 1; p_s = s; p_par = c_par; p_b = c_b; p_icount = c_icount;
         }
-        const T kq_i = P.ke * pi.w;
+    } else {
+        // =============================== consumer warps ===============================
+        const int sub4 = lane >> 3, l = lane & 7;
+        constexpr int LIST_HALF = (MB_LIST_BATCH >= 2) ? MB_LIST_BATCH / 2 : 1;
+        const int words_in_row = g.stride >> 5;  // groups a row can hold
+        // per-quad state (the stage pointers change from quad to quad)
+        const T4* s_pos = nullptr;
+        const T2* s_lj = nullptr;
+        uint32_t s_pos_u32 = 0;
+        T4 pi = make4<T>(0, 0, 0, 0);
+        T lj_s_i = (T)0, lj_e_i = (T)0, kq_i = (T)0;
         T fx = (T)0, fy = (T)0, fz = (T)0;
 #if MB_USE_F32X2
         float2 axx = make_float2(0.f, 0.f), ayy = axx, azz = axx;  // packed-f32 accumulators (two neighbours per lane)
@@ -170,16 +227,9 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 2 : MB_MIN_B
         };
         // four neighbours at once, stage by stage, so the four shared-memory loads and the four reciprocal
         // chains are independent and in flight together
-        auto eval4 = [&](uint2 w) {
-#if defined(MB_ABL) && MB_ABL == 1  // ablation: no pair work at all (staging + list streaming + bookkeeping only)
-            fx += __uint_as_float((w.x ^ w.y) & 0x3f000000u);
-            return;
-#endif
+        auto eval4 = [&](uint2 wd) {
             // entries are byte offsets of float4 records (halo index << LIST_SHIFT)
-            int j[4] = {(int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16)};
-#if defined(MB_ABL) && MB_ABL == 2  // ablation: arithmetic without the shared-memory gathers
-            j[0] = j[1] = j[2] = j[3] = (int)(threadIdx.x & 7) << LIST_SHIFT;
-#endif
+            const int j[4] = {(int)(wd.x & 0xffffu), (int)(wd.x >> 16), (int)(wd.y & 0xffffu), (int)(wd.y >> 16)};
             T4 pj[4];
             T2 lj[4];
 #pragma unroll
@@ -239,30 +289,95 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 2 : MB_MIN_B
             }
         };
 
-        // main list: groups of 32 entries; with LPA lanes each lane owns 32/LPA entries per group
-        const int n_groups = ((int)cnt.x + 31) >> 5;
-        const unsigned short* lp = list + (size_t)slot * g.stride;
-        // next task (if any): its list length is requested now, its first index words after the first half below
-        int nslot = 0, nsi = 0;
-        const bool nvalid = (it + 1 < n_iter) ? locate((it + 1) * NSUB + sub, nslot, nsi) : false;
-        ushort2 ncnt = nvalid ? counts[nslot] : make_ushort2(0, 0);
-        if (LPA == 8) {
-            const uint2* lp2 = reinterpret_cast<const uint2*>(lp) + l;
-            // second half of this task's first batch
+        // ---- quad hand-out ------------------------------------------------------------------------------------
+        int look_seq = 0;  // stage sequence number the hand-out cursor is in
+        int held_seq = 0;  // earliest stage this warp has not released yet
+        int k_local = 0;   // ENERGY: quads this warp already took from stage look_seq
+        struct QD { int seq, slot, si, n_main, n_spec; };
+        auto release_upto = [&](int upto) {  // this warp holds no quad in the stages before `upto` any more
+            __syncwarp();
+            if (lane == 0)
+                for (int q = held_seq; q < upto; q++) mbar_arrive(&s_empty[q % nbuf]);
+            held_seq = max(held_seq, upto);
+        };
+        // returns 1: quad found, 0: no more work, -1: the cursor would run more than the ring depth ahead of a held stage.
+        // holding: a quad of this warp is still in flight in stage held_seq (stages are then released after that quad).
+        auto lookup = [&](int max_seq, bool holding, QD& o) -> int {
+            for (;;) {
+                if (look_seq > max_seq) return -1;
+                const int s = look_seq % nbuf;
+                mbar_wait(&s_ready[s], (uint32_t)((look_seq / nbuf) & 1));
+                const int icount = s_meta[s].icount;
+                if (icount < 0) return 0;
+                int q;
+                if (ENERGY || sched == nullptr) {
+                    q = w + NW * k_local;
+                    k_local++;
+                } else {
+                    q = 0;
+                    if (lane == 0) q = atomicAdd(&s_meta[s].next_q, 1);
+                    q = __shfl_sync(0xffffffffu, q, 0);
+                }
+                if (q < s_meta[s].nq) {
+                    const int t = 4 * q + sub4;
+                    int2 e = make_int2(0, 0);
+                    if (t < icount) e = reinterpret_cast<const int2*>(smem_raw + (size_t)s * stage_bytes + task_off)[t];
+                    o.seq = look_seq;
+                    o.slot = (t < icount) ? e.x : -1;
+                    o.si = e.y & 0xfff;
+                    o.n_main = (e.y >> 12) & 0xfff;
+                    o.n_spec = (e.y >> 24) & 0xff;
+                    return 1;
+                }
+                look_seq++;
+                k_local = 0;
+                if (!holding) release_upto(look_seq);  // nothing in flight: pass exhausted stages on right away
+            }
+        };
+        uint2 wa[LIST_HALF];
+        auto request_first = [&](const QD& qd) {
+            const uint2* p2 = reinterpret_cast<const uint2*>(list + (size_t)max(qd.slot, 0) * g.stride) + l;
+#pragma unroll
+            for (int u = 0; u < LIST_HALF; u++)
+                wa[u] = (qd.slot >= 0 && u < words_in_row) ? ldg_stream_u2(p2 + (size_t)u * 8) : make_uint2(0u, 0u);
+        };
+        QD cur, nxt;
+        int r = lookup(0x7fffffff, false, cur);
+        if (r == 1) request_first(cur);
+        while (r == 1) {
+            {
+                unsigned char* st = smem_raw + (size_t)(cur.seq % nbuf) * stage_bytes;
+                s_pos = reinterpret_cast<const T4*>(st);
+                s_lj = reinterpret_cast<const T2*>(st + lj_off);
+                s_pos_u32 = smem_u32(st);
+            }
+            const bool valid = cur.slot >= 0;
+            const int slot = max(cur.slot, 0);
+            pi = s_pos[cur.si];
+            if (!UNIFORM) {
+                T2 t = s_lj[cur.si];
+                lj_s_i = t.x;
+                lj_e_i = t.y;
+            }
+            kq_i = P.ke * pi.w;
+            fx = (T)0; fy = (T)0; fz = (T)0;
+#if MB_USE_F32X2
+            axx = make_float2(0.f, 0.f); ayy = axx; azz = axx;
+#endif
+            // main list: groups of 32 entries; each of the 8 lanes owns 4 entries (one 8-byte word) per group
+            const int n_groups = (cur.n_main + 31) >> 5;
+            const uint2* lp2 = reinterpret_cast<const uint2*>(list + (size_t)slot * g.stride) + l;
+            // second half of this quad's first batch
             uint2 wb[LIST_HALF];
 #pragma unroll
             for (int u = 0; u < LIST_HALF; u++)
                 wb[u] = (LIST_HALF + u < n_groups) ? ldg_stream_u2(lp2 + (size_t)(LIST_HALF + u) * 8) : make_uint2(0u, 0u);
+            // the next quad (possibly in a later stage): descriptor now, its first index words after the first half below
+            r = lookup(cur.seq + nbuf - 1, true, nxt);
 #pragma unroll
             for (int u = 0; u < LIST_HALF; u++)
                 if (u < n_groups) eval4(wa[u]);
-            // prefetch the next task's first half into the registers just consumed
-            {
-                const uint2* np2 = reinterpret_cast<const uint2*>(list + (size_t)nslot * g.stride) + l;
-#pragma unroll
-                for (int u = 0; u < LIST_HALF; u++)
-                    wa[u] = (nvalid && u < words_in_row) ? ldg_stream_u2(np2 + (size_t)u * 8) : make_uint2(0u, 0u);
-            }
+            if (r == 1) request_first(nxt);
 #pragma unroll
             for (int u = 0; u < LIST_HALF; u++)
                 if (LIST_HALF + u < n_groups) eval4(wb[u]);
@@ -276,35 +391,34 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 2 : MB_MIN_B
                 for (int u = 0; u < LIST_HALF; u++)
                     if (g0 + u < n_groups) eval4(wc[u]);
             }
-        } else {
-            // generic: logical entry m of a group lives at ((m & 7) << 2) + (m >> 3)
-            for (int gi = 0; gi < n_groups; gi++) {
-                for (int m = l; m < 32; m += LPA) {
-                    int phys = ((m & 7) << 2) + (m >> 3);
-                    eval((int)lp[gi * 32 + phys] >> LIST_SHIFT, std::false_type{});
-                }
-            }
-        }
-        // special (1-4) pairs
-        for (int m = l; m < (int)cnt.y; m += LPA) eval((int)slist[(size_t)slot * g.sstride + m], std::true_type{});
+            // special (1-4) pairs
+            for (int m = l; m < cur.n_spec; m += 8) eval((int)slist[(size_t)slot * g.sstride + m], std::true_type{});
 #if MB_USE_F32X2
-        if constexpr (std::is_same<T, float>::value) {
-            fx += axx.x + axx.y;
-            fy += ayy.x + ayy.y;
-            fz += azz.x + azz.y;
-        }
+            if constexpr (std::is_same<T, float>::value) {
+                fx += axx.x + axx.y;
+                fy += ayy.x + ayy.y;
+                fz += azz.x + azz.y;
+            }
 #endif
-        // reduce the LPA partial forces
-        __syncwarp();
+            // reduce the 8 partial forces of every atom
+            __syncwarp();
 #pragma unroll
-        for (int o = LPA >> 1; o > 0; o >>= 1) {
-            fx += shfl_xor(fx, o);
-            fy += shfl_xor(fy, o);
-            fz += shfl_xor(fz, o);
+            for (int o = 4; o > 0; o >>= 1) {
+                fx += shfl_xor(fx, o);
+                fy += shfl_xor(fy, o);
+                fz += shfl_xor(fz, o);
+            }
+            if (l == 0 && valid) out.f4[slot] = make4<T>(fx, fy, fz, (T)0);
+            // release the stages this warp no longer holds a quad in
+            release_upto((r == 1) ? nxt.seq : look_seq);
+            if (r == -1) {  // the cursor stopped at the ring depth: nothing is held now, so waiting is safe
+                r = lookup(0x7fffffff, false, nxt);
+                if (r == 1) request_first(nxt);
+            }
+            cur = nxt;
         }
-        if (l == 0 && valid) out.f4[slot] = make4<T>(fx, fy, fz, (T)0);
-        slot = nslot; si = nsi; valid = nvalid; cnt = ncnt;
     }
+
     if (ENERGY) {
         // full shell: every pair was visited from both ends -> 1/2
         __shared__ double s_red[FORCE_THREADS / 32][7];
@@ -315,16 +429,24 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 2 : MB_MIN_B
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
         }
-        const int lane = tid & 31, wid = tid >> 5;
         if (lane == 0)
-            for (int k = 0; k < 7; k++) s_red[wid][k] = v[k];
+            for (int k = 0; k < 7; k++) s_red[w][k] = v[k];
         __syncthreads();
         if (tid < 7) {
             double s = 0.0;
-            for (int w = 0; w < FORCE_THREADS / 32; w++) s += s_red[w][tid];
+            for (int ww = 0; ww < FORCE_THREADS / 32; ww++) s += s_red[ww][tid];
             s *= 0.5;
-            if (tid == 0) out.pe_partial[b] = s;
-            else out.vir_partial[(size_t)b * 6 + (tid - 1)] = s;
+            if (tid == 0) out.pe_partial[blockIdx.x] = s;
+            else out.vir_partial[(size_t)blockIdx.x * 6 + (tid - 1)] = s;
+        }
+    }
+    if (!ENERGY && sched != nullptr && tid == FORCE_THREADS - 32) {
+        // the last CTA to get here re-arms the brick ticket for the next launch (every CTA has drawn its last ticket)
+        __threadfence();
+        const unsigned int t = atomicInc(sched + 1, gridDim.x - 1);
+        if (t == gridDim.x - 1) {  // (tickets count from gridDim.x: every CTA's first brick is its block index)
+            sched[0] = 0u;
+            __threadfence();
         }
     }
 }

@@ -62,7 +62,7 @@ template <typename T>
 struct PeerPush {
     int n_seg;
     int start[MB_MAX_SEG], count[MB_MAX_SEG];
-    typename VT<T>::T4* dst[MB_MAX_SEG];  // peer's pos4 base (same slot indexing)
+    typename VT<T>::T4* dst[MB_MAX_SEG];  // peer's extended position array pos4e (same indexing: the cell sort is replicated)
     int n_peer;
     const unsigned long long* wait_flag[MB_MAX_SEG];  // my comm->read_epoch[peer]
     unsigned long long* signal_flag[MB_MAX_SEG];      // peer comm->halo_epoch[me]

@@ -46,8 +46,7 @@ template <typename T>
 __global__ void ingest_kernel(int n, Geom<T> g, const T* __restrict__ coords, const T* __restrict__ vels,
                               const int* __restrict__ orig, const typename VT<T>::T4* __restrict__ xref4,
                               typename VT<T>::T4* __restrict__ pos4, typename VT<T>::T4* __restrict__ vel4,
-                              int* __restrict__ flag, const typename VT<T>::T4* __restrict__ xprune4 = nullptr,
-                              int* __restrict__ prune_flag = nullptr) {
+                              int* __restrict__ flag) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int o = orig[s];
@@ -73,18 +72,6 @@ __global__ void ingest_kernel(int n, Geom<T> g, const T* __restrict__ coords, co
         vel4[s] = v;
     }
     if (d2 > g.skin_half2) *flag = 1;
-    if (xprune4) {
-        const typename VT<T>::T4 rp = xprune4[s];
-        T e2 = (T)0;
-        const T xr[3] = {rp.x, rp.y, rp.z};
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            T dd = x[d] - xr[d];
-            dd -= g.L[d] * frint(dd * g.invL[d]);
-            e2 += dd * dd;
-        }
-        if (e2 > g.skin_in_half2) *prune_flag = 1;
-    }
 }
 
 // ---- export: slot order -> original order, wrapped coordinates, pending CM velocity applied ----
@@ -149,9 +136,7 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
                                      const typename VT<T>::T4* __restrict__ f4,
                                      const typename VT<T>::T4* __restrict__ xref4, typename VT<T>::T4* __restrict__ pos4,
                                      typename VT<T>::T4* __restrict__ vel4, int* __restrict__ flag, Control* __restrict__ ctl,
-                                     cudaGraphConditionalHandle handle, int use_handle,
-                                     const typename VT<T>::T4* __restrict__ xprune4, T skin_in_half2,
-                                     cudaGraphConditionalHandle handle_prune, PeerPush<T> push) {
+                                     cudaGraphConditionalHandle handle, int use_handle, PeerPush<T> push, ExtMap<T> ext) {
     bool cmv = cm->valid != 0;
     T cx = cm->v[0], cy = cm->v[1], cz = cm->v[2];
     if (push.n_peer > 0 || push.cm_nranks > 0) {  // decomposed run over peer memory (peer.cuh)
@@ -177,7 +162,7 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
             cx = (T)s_cm[0]; cy = (T)s_cm[1]; cz = (T)s_cm[2];
         }
     }
-    bool moved = false, moved_in = false;
+    bool moved = false;
     float d2max = 0.f;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int s = s0 + k;  // [s0, s0 + n): the slots this rank owns
@@ -191,20 +176,18 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
         p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
         vel4[s] = v;
         pos4[s] = p;
-        for (int q = 0; q < push.n_seg; q++)  // halo exchange fused into the drift: mirror boundary slots into the peers
-            if ((unsigned int)(s - push.start[q]) < (unsigned int)push.count[q]) push.dst[q][s] = p;
+        if (ext.pos4e) {
+            // extended (ghost-padded) array the force kernel stages from: own entry + periodic-image copies
+            ext_store<T>(ext, s, p, ext.pos4e);
+            for (int q = 0; q < push.n_seg; q++)  // halo exchange fused into the drift: mirror boundary slots into the peers
+                if ((unsigned int)(s - push.start[q]) < (unsigned int)push.count[q]) ext_store<T>(ext, s, p, push.dst[q]);
+        }
         const T dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
         const T d2 = dx * dx + dy * dy + dz * dz;
         moved |= (d2 > skin_half2);
         d2max = fmaxf(d2max, (float)d2);
-        if (xprune4) {  // dual list: displacement since the last prune against half the inner skin
-            const typename VT<T>::T4 rp = xprune4[s];
-            const T ex = p.x - rp.x, ey = p.y - rp.y, ez = p.z - rp.z;
-            moved_in |= (ex * ex + ey * ey + ez * ez > skin_in_half2);
-        }
     }
     if (moved) *flag = 1;
-    if (moved_in) ctl->prune = 1;
     for (int o = 16; o > 0; o >>= 1) d2max = fmaxf(d2max, __shfl_xor_sync(0xffffffffu, d2max, o));
     __shared__ float s_d2[32];
     __shared__ bool s_last;
@@ -228,10 +211,7 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
         const long long kk = step_n - ctl->init_step;
         int rb = *(volatile int*)&ctl->rebuild;
         if (ctl->rebuild_every > 0 && kk > 1 && (step_n - 1) % ctl->rebuild_every == 0) { rb = 1; ctl->rebuild = 1; }
-        if (use_handle) {
-            cudaGraphSetConditional(handle, rb ? 1u : 0u);
-            if (xprune4) cudaGraphSetConditional(handle_prune, (rb || *(volatile int*)&ctl->prune) ? 1u : 0u);
-        }
+        if (use_handle) cudaGraphSetConditional(handle, rb ? 1u : 0u);
         if (push.n_peer > 0) {  // every CTA's peer stores are ordered before its ticket: publish the epoch
             __threadfence_system();
             for (int q = 0; q < push.n_peer; q++) st_release_sys(push.signal_flag[q], push.epoch);

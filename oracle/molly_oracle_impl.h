@@ -158,6 +158,26 @@ static inline void FN(pair_eval)(const orc_inter_t *in, const FN(pairparm) * p, 
             f = f - fc;
             e = e + (r - rc) * fc - ec;
             if (!(r <= rc)) { f = 0; e = 0; }
+        } else if (in->cutoff_kind == ORC_CUT_CUBIC_SPLINE || in->cutoff_kind == ORC_CUT_POLYNOMIAL) {
+            /* two-point cutoffs on V = kqq / r (generic force_cutoff / pe_cutoff, cutoffs.jl:23-29, :39-45) */
+            REAL ra = (REAL)in->r_act;
+            if (!(r <= ra)) {
+                REAL t = (r - ra) / (rc - ra);
+                if (in->cutoff_kind == ORC_CUT_CUBIC_SPLINE) { /* cutoffs.jl:192-215 */
+                    REAL pe_act = kqq * (1 / ra);
+                    REAL dpe_act = -(kqq / (ra * ra));
+                    e = (2 * t * t * t - 3 * t * t + 1) * pe_act + (t * t * t - 2 * t * t + t) * (rc - ra) * dpe_act;
+                    f = -(6 * t * t - 6 * t) * pe_act / (rc - ra) - (3 * t * t - 4 * t + 1) * dpe_act;
+                } else { /* PolynomialCutoff, cutoffs.jl:241-253 */
+                    REAL t2 = t * t, t3 = t2 * t;
+                    REAL S = 1 - 6 * t3 * t2 + 15 * t2 * t2 - 10 * t3;
+                    REAL dS = (-30 * t2 * t2 + 60 * t3 - 30 * t2) / (rc - ra);
+                    REAL f0 = f, e0 = e;
+                    e = S * e0;
+                    f = S * f0 - dS * e0;
+                }
+                if (!(r <= rc)) { f = 0; e = 0; }
+            }
         }
         fr = (f / r) * w;
         pe = e * w;
@@ -340,8 +360,8 @@ int FN(orc_forces_allpairs)(const orc_system_t *s, const void *coords_v, void *f
  * r_list are not exercised by the reference's tests).
  * Returns number of entries; *out is malloc'd (free with orc_free).
  */
-int64_t FN(orc_neighbor_list)(const orc_system_t *s, const void *coords_v, double r_list,
-                              orc_nl_entry_t **out) {
+int64_t FN(orc_neighbor_list_mt)(const orc_system_t *s, const void *coords_v, double r_list,
+                                 orc_nl_entry_t **out, int n_threads_nl) {
     const REAL *coords = (const REAL *)coords_v;
     int64_t n = s->n_atoms;
     int nc[3];
@@ -373,55 +393,85 @@ int64_t FN(orc_neighbor_list)(const orc_system_t *s, const void *coords_v, doubl
     for (int64_t i = 0; i < n; i++) sorted[fill[cell_of[i]]++] = (int32_t)i;
     free(fill);
 
-    int64_t cap = n * 64 + 1024, cnt = 0;
-    orc_nl_entry_t *list = (orc_nl_entry_t *)malloc(sizeof(orc_nl_entry_t) * cap);
+    /* The pair search is threaded like the reference's (CellListMap.map_pairwise! with parallel = n_threads > 1,
+     * src/neighbors.jl:676-680): contiguous blocks of atoms are claimed by threads, every block fills its own buffer,
+     * and the buffers are concatenated in block order, so the list is the same as a serial scan's whatever the
+     * thread count. */
     double rl2 = r_list * r_list;
-    /* distinct neighbour cells per dimension (handles nc < 3 without double counting) */
-    for (int64_t i = 0; i < n; i++) {
-        int32_t ci = cell_of[i];
-        int cx = ci % nc[0], cy = (ci / nc[0]) % nc[1], cz = ci / (nc[0] * nc[1]);
-        int lst[3][3], ln[3];
-        int cc[3] = {cx, cy, cz};
-        for (int d = 0; d < 3; d++) {
-            ln[d] = 0;
-            for (int o = -1; o <= 1; o++) {
-                int v = (cc[d] + o + nc[d]) % nc[d];
-                int dup = 0;
-                for (int k = 0; k < ln[d]; k++) dup |= (lst[d][k] == v);
-                if (!dup) lst[d][ln[d]++] = v;
-            }
-        }
-        for (int a = 0; a < ln[2]; a++)
-            for (int b = 0; b < ln[1]; b++)
-                for (int c = 0; c < ln[0]; c++) {
-                    int64_t cj = ((int64_t)lst[2][a] * nc[1] + lst[1][b]) * nc[0] + lst[0][c];
-                    for (int64_t k = cstart[cj]; k < cstart[cj + 1]; k++) {
-                        int32_t j = sorted[k];
-                        if (j <= i) continue;
-                        double d2 = 0;
-                        for (int d = 0; d < 3; d++) {
-                            double v = (double)FN(vector_1D)(coords[3 * i + d], coords[3 * (int64_t)j + d],
-                                                             (REAL)s->box[d]);
-                            d2 += v * v;
-                        }
-                        if (d2 > rl2) continue;
-                        if (FN(csr_has)(s->excl_ptr, s->excl_idx, (int32_t)i, j)) continue;
-                        if (cnt == cap) {
-                            cap *= 2;
-                            list = (orc_nl_entry_t *)realloc(list, sizeof(orc_nl_entry_t) * cap);
-                        }
-                        list[cnt].i = (int32_t)i;
-                        list[cnt].j = j;
-                        list[cnt].special = FN(csr_has)(s->spec_ptr, s->spec_idx, (int32_t)i, j);
-                        cnt++;
-                    }
+    int nthr = n_threads_nl > 0 ? n_threads_nl : omp_get_max_threads();
+    if (nthr < 1) nthr = 1;
+    int64_t nblk = (int64_t)nthr * 8;
+    if (nblk > n) nblk = n > 0 ? n : 1;
+    orc_nl_entry_t **bbuf = (orc_nl_entry_t **)calloc(nblk, sizeof(orc_nl_entry_t *));
+    int64_t *bcnt = (int64_t *)calloc(nblk + 1, sizeof(int64_t));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthr)
+    for (int64_t blk = 0; blk < nblk; blk++) {
+        int64_t i0 = n * blk / nblk, i1 = n * (blk + 1) / nblk;
+        int64_t cap = (i1 - i0) * 64 + 1024, cnt = 0;
+        orc_nl_entry_t *list = (orc_nl_entry_t *)malloc(sizeof(orc_nl_entry_t) * cap);
+        /* distinct neighbour cells per dimension (handles nc < 3 without double counting) */
+        for (int64_t i = i0; i < i1; i++) {
+            int32_t ci = cell_of[i];
+            int cx = ci % nc[0], cy = (ci / nc[0]) % nc[1], cz = ci / (nc[0] * nc[1]);
+            int lst[3][3], ln[3];
+            int cc[3] = {cx, cy, cz};
+            for (int d = 0; d < 3; d++) {
+                ln[d] = 0;
+                for (int o = -1; o <= 1; o++) {
+                    int v = (cc[d] + o + nc[d]) % nc[d];
+                    int dup = 0;
+                    for (int k = 0; k < ln[d]; k++) dup |= (lst[d][k] == v);
+                    if (!dup) lst[d][ln[d]++] = v;
                 }
+            }
+            for (int a = 0; a < ln[2]; a++)
+                for (int b = 0; b < ln[1]; b++)
+                    for (int c = 0; c < ln[0]; c++) {
+                        int64_t cj = ((int64_t)lst[2][a] * nc[1] + lst[1][b]) * nc[0] + lst[0][c];
+                        for (int64_t k = cstart[cj]; k < cstart[cj + 1]; k++) {
+                            int32_t j = sorted[k];
+                            if (j <= i) continue;
+                            double d2 = 0;
+                            for (int d = 0; d < 3; d++) {
+                                double v = (double)FN(vector_1D)(coords[3 * i + d], coords[3 * (int64_t)j + d],
+                                                                 (REAL)s->box[d]);
+                                d2 += v * v;
+                            }
+                            if (d2 > rl2) continue;
+                            if (FN(csr_has)(s->excl_ptr, s->excl_idx, (int32_t)i, j)) continue;
+                            if (cnt == cap) {
+                                cap *= 2;
+                                list = (orc_nl_entry_t *)realloc(list, sizeof(orc_nl_entry_t) * cap);
+                            }
+                            list[cnt].i = (int32_t)i;
+                            list[cnt].j = j;
+                            list[cnt].special = FN(csr_has)(s->spec_ptr, s->spec_idx, (int32_t)i, j);
+                            cnt++;
+                        }
+                    }
+        }
+        bbuf[blk] = list;
+        bcnt[blk + 1] = cnt;
     }
+    for (int64_t blk = 0; blk < nblk; blk++) bcnt[blk + 1] += bcnt[blk];
+    int64_t cnt = bcnt[nblk];
+    orc_nl_entry_t *list = (orc_nl_entry_t *)malloc(sizeof(orc_nl_entry_t) * (cnt > 0 ? cnt : 1));
+#pragma omp parallel for schedule(static) num_threads(nthr)
+    for (int64_t blk = 0; blk < nblk; blk++) {
+        memcpy(list + bcnt[blk], bbuf[blk], sizeof(orc_nl_entry_t) * (bcnt[blk + 1] - bcnt[blk]));
+        free(bbuf[blk]);
+    }
+    free(bbuf);
+    free(bcnt);
     free(cell_of);
     free(cstart);
     free(sorted);
     *out = list;
     return cnt;
+}
+
+int64_t FN(orc_neighbor_list)(const orc_system_t *s, const void *coords_v, double r_list, orc_nl_entry_t **out) {
+    return FN(orc_neighbor_list_mt)(s, coords_v, r_list, out, 0);
 }
 
 /*
@@ -535,7 +585,7 @@ int FN(orc_simulate_vv)(const orc_system_t *s, void *coords_v, void *vel_v, doub
     for (int64_t i = 0; i < n; i++)
         for (int d = 0; d < 3; d++) x[3 * i + d] = FN(wrap_coord_1D)(x[3 * i + d], (REAL)s->box[d]);
     if (remove_cm_every) FN(orc_remove_cm)(s, v);
-    if (r_list > 0) n_list = FN(orc_neighbor_list)(s, x, r_list, &list);
+    if (r_list > 0) n_list = FN(orc_neighbor_list_mt)(s, x, r_list, &list, n_threads);
 #define ORC_FORCE_EVAL()                                                                              \
     do {                                                                                              \
         memset(f, 0, sizeof(REAL) * 3 * n);                                                           \
@@ -563,7 +613,7 @@ int FN(orc_simulate_vv)(const orc_system_t *s, void *coords_v, void *vel_v, doub
         if (remove_cm_every && step % remove_cm_every == 0) FN(orc_remove_cm)(s, v);
         if (r_list > 0 && nl_every > 0 && step % nl_every == 0) {
             free(list);
-            n_list = FN(orc_neighbor_list)(s, x, r_list, &list);
+            n_list = FN(orc_neighbor_list_mt)(s, x, r_list, &list, n_threads);
         }
     }
     if (pe_final) {

@@ -1,6 +1,5 @@
 """csrc/cutoffs2.cuh (CubicSplineCutoff / PolynomialCutoff) compiled for the HOST and checked against
-the reference's literals (test/interactions.jl:1574-1603) and the C oracle. The header is prepared but not wired into the
-pair kernels yet (see its status note), so there is no GPU counterpart of this test."""
+the reference's literals (test/interactions.jl:1574-1603) and the C oracle. The GPU counterpart is tests/test_gpu_parity.py::test_two_point_cutoffs_*."""
 import ctypes as C
 import os
 import shutil
@@ -59,6 +58,22 @@ def test_two_point_cutoffs_on_host(hostlib):
         assert abs(below[0] - above[0]) < 1e-6 and abs(below[1] - above[1]) < 1e-8
         end = _lj(hostlib, kind, ra, rc, 0.3, 0.2, rc)
         assert abs(end[0]) < 1e-12 and abs(end[1]) < 1e-12
+    # Coulomb flavour: same switch on V = kqq / r, against the oracle's Coulomb branch over the whole range
+    ke = 138.93545764
+    for kind, okind in ((4, o.CUT_CUBIC_SPLINE), (5, o.CUT_POLYNOMIAL)):
+        for _ in range(200):
+            qi, qj = rng.uniform(-1, 1, 2)
+            ra = rng.uniform(0.5, 0.9)
+            rc = ra + rng.uniform(0.05, 0.4)
+            r = rng.uniform(0.3, rc * 1.1)
+            s = o.OracleSystem(box=np.array([6.0, 6.0, 6.0]), mass=np.ones(2), charge=np.array([qi, qj]), sigma=np.zeros(2),
+                               eps=np.zeros(2), inters=[o.Inter(o.COULOMB, okind, rc, r_act=ra)])
+            f, e_ref, _ = s.forces_allpairs(np.array([[1.0, 1.0, 1.0], [1.0 + r, 1.0, 1.0]]))
+            fr, e = C.c_double(), C.c_double()
+            hostlib.cut2h_coul(kind, C.c_double(ra), C.c_double(rc), C.c_double(ke * qi * qj), C.c_double(r), C.byref(fr), C.byref(e))
+            frv, ev = (fr.value, e.value) if r <= rc else (0.0, 0.0)  # the caller applies the r <= r_c test
+            assert abs(frv * r - f[1, 0]) < 1e-9 * max(1.0, abs(f[1, 0]))
+            assert abs(ev - e_ref) < 1e-10 * max(1.0, abs(e_ref))
     # Coulomb flavour: same switch on V = kqq / r
     fr, e = C.c_double(), C.c_double()
     hostlib.cut2h_coul(5, C.c_double(0.6), C.c_double(0.8), C.c_double(138.93545764), C.c_double(0.8), C.byref(fr), C.byref(e))

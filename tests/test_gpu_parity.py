@@ -676,7 +676,7 @@ def test_two_point_cutoffs_brick_and_allpairs(dtype, cut):
     sd = H.molecular_system(1000, [5.1, 5.4, 5.8], seed=5)
     _check(sd, mi, oi, dtype, r_list=1.1, expect_path=1, label=f"molecular brick {cut}")
     sd = H.molecular_system(150, [3.0, 3.2, 3.4], seed=11)
-    _check(sd, mi, oi, dtype, r_list=1.1, expect_path=0, label=f"molecular all-pairs {cut}")
+    _check(sd, mi, oi, dtype, r_list=1.25, expect_path=0, label=f"molecular all-pairs {cut}")  # 3.0 nm < 2.5 r_list: no-list kernel
     sd = H.lj_fluid(9, seed=42, dtype=np.float64)
     _check(sd, (mb.LennardJones(cutoff=mcut, use_neighbors=True),), [o.Inter(o.LJ, ocut, 1.0, r_act=0.8, use_neighbors=True)],
            dtype, r_list=1.1, expect_path=1, label=f"LJ fluid {cut} (uniform)")
