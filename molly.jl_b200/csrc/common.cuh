@@ -114,6 +114,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+// slow path of a wait whose first try failed (kept out of line: the hot loops only carry the try)
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 // global -> shared bulk copy; src/dst 16-byte aligned, bytes a multiple of 16
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -136,12 +138,37 @@ __device__ __forceinline__ dbl4 lds_pos(uint32_t addr, double) {
     return r;
 }
 
+// LJ parameter pair (sigma part, eps part) at a 32-bit shared-memory address
+__device__ __forceinline__ float2 lds_pair(uint32_t addr, float) {
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ dbl2 lds_pair(uint32_t addr, double) {
+    dbl2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+    return r;
+}
+
 // streaming (read-once) global loads that do not pollute L1
 __device__ __forceinline__ uint2 ldg_stream_u2(const uint2* p) {
     uint2 r;
+#if defined(MB_ABL_NOLIST)  // ablation: no neighbour-list loads (indices derived from the address: wrong results, timing only)
+    const unsigned int a = (unsigned int)((unsigned long long)p >> 3);
+    r.x = ((a * 2654435761u) >> 19 & 0x1ff0u) | (((a * 40503u) & 0x1ff0u) << 16);
+    r.y = ((a * 97u) & 0x1ff0u) | (((a * 31u) & 0x1ff0u) << 16);
+    return r;
+#endif
+#if defined(MB_LDG_PLAIN)
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+#elif defined(MB_LDG_NC)
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+#endif
     return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // warp helpers
 template <typename T>

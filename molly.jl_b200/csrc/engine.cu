@@ -730,9 +730,9 @@ class Engine : public EngineBase {
         const size_t stage = force_stage();
         const size_t sm_total = smem_optin_ + 1024;  // 228 KB per SM, 1 KB reserved per resident CTA
         const size_t static_bytes = 1024;
-        ctas_per_sm = (sizeof(T) == 8) ? 1 : 2;
-        if (ctas_per_sm == 2 && (sm_total / 2 - 1024 - static_bytes) / stage < 1) ctas_per_sm = 1;
-        const size_t budget = (ctas_per_sm == 2) ? sm_total / 2 - 1024 - static_bytes : smem_optin_ - static_bytes;
+        ctas_per_sm = (sizeof(T) == 8) ? 1 : FORCE_CTAS_F32;
+        while (ctas_per_sm > 1 && (sm_total / ctas_per_sm - 1024 - static_bytes) / stage < 1) ctas_per_sm--;
+        const size_t budget = (ctas_per_sm > 1) ? sm_total / ctas_per_sm - 1024 - static_bytes : smem_optin_ - static_bytes;
         nbuf = (int)std::min<size_t>(FORCE_MAX_STAGES, std::max<size_t>(1, budget / stage));
         if (const char* e = getenv("MOLLYB200_NBUF")) nbuf = std::max(1, std::min(nbuf, atoi(e)));  // tuning aid: shallower ring
     }

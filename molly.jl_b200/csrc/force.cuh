@@ -22,7 +22,14 @@ namespace mb {
 // ---- launch shape of the persistent brick kernel ---------------------------------------------------------------
 // 16 warps per CTA: 15 consumer warps evaluate pairs, 1 producer warp feeds them through a ring of up to FORCE_MAX_STAGES
 // shared-memory stages (one stage = one brick's halo + its task table), filled by the TMA engine.
-constexpr int FORCE_THREADS = 512;
+#ifndef MB_FORCE_THREADS
+#define MB_FORCE_THREADS 512
+#endif
+#ifndef MB_FORCE_CTAS
+#define MB_FORCE_CTAS 2  // resident CTAs per SM the f32 variants are compiled for (register cap = 64K / (CTAs x threads))
+#endif
+constexpr int FORCE_THREADS = MB_FORCE_THREADS;
+constexpr int FORCE_CTAS_F32 = MB_FORCE_CTAS;
 constexpr int FORCE_CONSUMER_WARPS = FORCE_THREADS / 32 - 1;
 constexpr int FORCE_MAX_STAGES = 3;
 #ifndef MB_LIST_BATCH
@@ -40,7 +47,7 @@ struct ForceOut {
     PeerWait gate;            // decomposed run over peer memory: epoch flags the halo data of this step arrives under
 };
 
-struct StageMeta {
+struct __align__(16) StageMeta {
     int brick;    // global brick index staged here
     int icount;   // owned atoms (tasks) of the brick; -1 = no more work for this CTA
     int nq;       // quads of 4 tasks
@@ -68,7 +75,7 @@ __host__ __device__ inline size_t force_stage_bytes(int halo_cap, int task_cap, 
 //     evaluated, across stage boundaries), reduce with shuffles and store. A warp releases a stage (mbarrier empty[s])
 //     once it holds no quad in it; there is no CTA-wide barrier in the steady state.
 template <typename T, int COUL, bool UNIFORM, int CUTM, bool ENERGY>
-__global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
+__global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : FORCE_CTAS_F32)
     brick_force_kernel(Geom<T> g, PairParams<T> P, const BrickHdr* __restrict__ hdrs, const Run* __restrict__ runs,
                        const int2* __restrict__ task_tab, const typename VT<T>::T4* __restrict__ pos4e,
                        const typename VT<T>::T2* __restrict__ lj2e, const unsigned short* __restrict__ list,
@@ -125,8 +132,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
             }
             pend = 0;
         };
-        for (int seq = 0;; seq++) {
-            const int s = seq % nbuf, use = seq / nbuf;
+        for (int seq = 0, s = 0, use = 0;; seq++, s = (s + 1 == nbuf) ? 0 : s + 1, use += (s == 0) ? 1 : 0) {
             // (1) next brick: the first one of a CTA is its block index (no ticket latency in front of the first stage), the
             //     others are drawn from the global ticket counter; static round-robin when the launch asks for it
             int bi;
@@ -142,7 +148,14 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
             const bool last = bi >= nbr;
             const int c_b = brick0 + (last ? 0 : bi);
             BrickHdr hd = {0, 0, 0u, 0u, 0, {0, 0, 0}};
-            if (!last) hd = hdrs[c_b];  // in flight while the previous stage lands
+            // header and this lane's first run entries: requested together, in flight while the previous stage lands
+            const Run* my_runs = runs + (size_t)c_b * g.max_runs;
+            Run pre[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+            if (!last) {
+                hd = hdrs[c_b];
+                if (lane < g.max_runs) pre[0] = my_runs[lane];
+                if (lane + 32 < g.max_runs) pre[1] = my_runs[lane + 32];
+            }
             // (2) publish the stage issued one round earlier. This comes BEFORE waiting for a free stage: a consumer may hold
             //     stage k while it waits for stage k + nbuf - 1 to be published.
             if (pend) publish();
@@ -170,9 +183,8 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
                 full_bits ^= 1u << s;
                 if (lane == 0) mbar_arrive_expect_tx(&s_full[s], hd.tx_pos + (UNIFORM ? 0u : hd.tx_lj) + tbytes);
                 __syncwarp();
-                const Run* my_runs = runs + (size_t)c_b * g.max_runs;
-                for (int r = lane; r < g.max_runs; r += 32) {
-                    const Run run = my_runs[r];
+                for (int r = lane, k = 0; r < g.max_runs; r += 32, k++) {
+                    const Run run = (k == 0) ? pre[0] : ((k == 1) ? pre[1] : my_runs[r]);
                     if (run.count > 0) {
                         bulk_g2s(&sp[run.soff], &pos4e[run.gstart], (uint32_t)run.count * (uint32_t)sizeof(T4), &s_full[s]);
                         if (!UNIFORM) {
@@ -191,10 +203,8 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
         const int sub4 = lane >> 3, l = lane & 7;
         constexpr int LIST_HALF = (MB_LIST_BATCH >= 2) ? MB_LIST_BATCH / 2 : 1;
         const int words_in_row = g.stride >> 5;  // groups a row can hold
-        // per-quad state (the stage pointers change from quad to quad)
-        const T4* s_pos = nullptr;
-        const T2* s_lj = nullptr;
-        uint32_t s_pos_u32 = 0;
+        // per-quad state (the stage changes from quad to quad): shared-memory addresses of the staged positions / LJ pairs
+        uint32_t s_pos_u32 = 0, s_lj_u32 = 0;
         T4 pi = make4<T>(0, 0, 0, 0);
         T lj_s_i = (T)0, lj_e_i = (T)0, kq_i = (T)0;
         T fx = (T)0, fy = (T)0, fz = (T)0;
@@ -204,10 +214,10 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
 #endif
         auto eval = [&](int j, auto special_tag) {
             constexpr bool SPECIAL = decltype(special_tag)::value;
-            const T4 pj = s_pos[j];
+            const T4 pj = lds_pos(s_pos_u32 + (uint32_t)j * (uint32_t)sizeof(T4), (T)0);
             T lj_s_j = (T)0, lj_e_j = (T)0;
             if (!UNIFORM) {
-                T2 t = s_lj[j];
+                T2 t = lds_pair(s_lj_u32 + (uint32_t)j * (uint32_t)sizeof(T2), (T)0);
                 lj_s_j = t.x;
                 lj_e_j = t.y;
             }
@@ -229,14 +239,18 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
         // chains are independent and in flight together
         auto eval4 = [&](uint2 wd) {
             // entries are byte offsets of float4 records (halo index << LIST_SHIFT)
+#ifdef MB_ABL_NOGATHER  // ablation: conflict-free gathers (every lane reads the record at its own lane index)
+            const int jj = (int)((threadIdx.x & 31u) << 4) + (int)((wd.x ^ wd.y) & 0x10u);
+            const int j[4] = {jj, jj, jj, jj};
+#else
             const int j[4] = {(int)(wd.x & 0xffffu), (int)(wd.x >> 16), (int)(wd.y & 0xffffu), (int)(wd.y >> 16)};
+#endif
             T4 pj[4];
             T2 lj[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 pj[u] = lds_pos(s_pos_u32 + (uint32_t)j[u] * (uint32_t)(sizeof(T4) >> LIST_SHIFT), (T)0);
-                if (!UNIFORM)
-                    lj[u] = *reinterpret_cast<const T2*>(reinterpret_cast<const char*>(s_lj) + (((size_t)j[u] * sizeof(T2)) >> LIST_SHIFT));
+                if (!UNIFORM) lj[u] = lds_pair(s_lj_u32 + (((uint32_t)j[u] * (uint32_t)sizeof(T2)) >> LIST_SHIFT), (T)0);
             }
 #if MB_USE_F32X2
             if constexpr (std::is_same<T, float>::value && UNIFORM && CUTM == CUTM_PLAIN && !ENERGY && COUL == COUL_NONE) {
@@ -290,46 +304,52 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
         };
 
         // ---- quad hand-out ------------------------------------------------------------------------------------
-        int look_seq = 0;  // stage sequence number the hand-out cursor is in
-        int held_seq = 0;  // earliest stage this warp has not released yet
-        int k_local = 0;   // ENERGY: quads this warp already took from stage look_seq
-        struct QD { int seq, slot, si, n_main, n_spec; };
+        // The cursor (look_*) walks the stages in publication order; (seq, s, par) = sequence number, ring index and
+        // mbarrier phase parity of a stage, advanced together (no division in the loop). held_* = earliest stage this
+        // warp has not released yet.
+        int look_seq = 0, look_s = 0;
+        uint32_t look_par = 0;
+        int held_seq = 0, held_s = 0;
+        int k_local = 0;   // static hand-out: quads this warp already took from stage look_seq
+        struct QD { int seq, slot, packed; uint32_t base; };  // packed = staged index | rows' lengths (task_pack); base = stage address
         auto release_upto = [&](int upto) {  // this warp holds no quad in the stages before `upto` any more
             __syncwarp();
-            if (lane == 0)
-                for (int q = held_seq; q < upto; q++) mbar_arrive(&s_empty[q % nbuf]);
-            held_seq = max(held_seq, upto);
+            while (held_seq < upto) {
+                if (lane == 0) mbar_arrive(&s_empty[held_s]);
+                held_s = (held_s + 1 == nbuf) ? 0 : held_s + 1;
+                held_seq++;
+            }
         };
         // returns 1: quad found, 0: no more work, -1: the cursor would run more than the ring depth ahead of a held stage.
         // holding: a quad of this warp is still in flight in stage held_seq (stages are then released after that quad).
         auto lookup = [&](int max_seq, bool holding, QD& o) -> int {
             for (;;) {
                 if (look_seq > max_seq) return -1;
-                const int s = look_seq % nbuf;
-                mbar_wait(&s_ready[s], (uint32_t)((look_seq / nbuf) & 1));
-                const int icount = s_meta[s].icount;
-                if (icount < 0) return 0;
+                if (!mbar_try_wait(&s_ready[look_s], look_par)) mbar_wait_slow(&s_ready[look_s], look_par);
+                const int4 mt = *reinterpret_cast<const int4*>(&s_meta[look_s]);  // brick, icount, nq, next_q
+                if (mt.y < 0) return 0;
                 int q;
                 if (ENERGY || sched == nullptr) {
                     q = w + NW * k_local;
                     k_local++;
                 } else {
                     q = 0;
-                    if (lane == 0) q = atomicAdd(&s_meta[s].next_q, 1);
+                    if (lane == 0) q = atomicAdd(&s_meta[look_s].next_q, 1);
                     q = __shfl_sync(0xffffffffu, q, 0);
                 }
-                if (q < s_meta[s].nq) {
+                if (q < mt.z) {
                     const int t = 4 * q + sub4;
-                    int2 e = make_int2(0, 0);
-                    if (t < icount) e = reinterpret_cast<const int2*>(smem_raw + (size_t)s * stage_bytes + task_off)[t];
+                    int2 e = make_int2(-1, 0);
+                    if (t < mt.y) e = reinterpret_cast<const int2*>(smem_raw + (size_t)look_s * stage_bytes + task_off)[t];
                     o.seq = look_seq;
-                    o.slot = (t < icount) ? e.x : -1;
-                    o.si = e.y & 0xfff;
-                    o.n_main = (e.y >> 12) & 0xfff;
-                    o.n_spec = (e.y >> 24) & 0xff;
+                    o.base = smem_u32(smem_raw) + (uint32_t)look_s * (uint32_t)stage_bytes;
+                    o.slot = e.x;
+                    o.packed = e.y;
                     return 1;
                 }
                 look_seq++;
+                look_s++;
+                if (look_s == nbuf) { look_s = 0; look_par ^= 1u; }
                 k_local = 0;
                 if (!holding) release_upto(look_seq);  // nothing in flight: pass exhausted stages on right away
             }
@@ -337,6 +357,9 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
         uint2 wa[LIST_HALF];
         auto request_first = [&](const QD& qd) {
             const uint2* p2 = reinterpret_cast<const uint2*>(list + (size_t)max(qd.slot, 0) * g.stride) + l;
+#ifdef MB_L2PF  // experiment: the second half of the row towards L2 while the first half is on its way to registers
+            if (qd.slot >= 0 && l < 2) prefetch_l2(reinterpret_cast<const char*>(p2) - l * 8 + 256 + l * 128);
+#endif
 #pragma unroll
             for (int u = 0; u < LIST_HALF; u++)
                 wa[u] = (qd.slot >= 0 && u < words_in_row) ? ldg_stream_u2(p2 + (size_t)u * 8) : make_uint2(0u, 0u);
@@ -345,17 +368,16 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
         int r = lookup(0x7fffffff, false, cur);
         if (r == 1) request_first(cur);
         while (r == 1) {
-            {
-                unsigned char* st = smem_raw + (size_t)(cur.seq % nbuf) * stage_bytes;
-                s_pos = reinterpret_cast<const T4*>(st);
-                s_lj = reinterpret_cast<const T2*>(st + lj_off);
-                s_pos_u32 = smem_u32(st);
-            }
+            s_pos_u32 = cur.base;
+            s_lj_u32 = cur.base + (uint32_t)lj_off;
             const bool valid = cur.slot >= 0;
             const int slot = max(cur.slot, 0);
-            pi = s_pos[cur.si];
+            const int cur_si = cur.packed & 0xfff, cur_n_main = (cur.packed >> 12) & 0xfff;
+            const int cur_n_spec = (int)((unsigned int)cur.packed >> 24);
+            pi = lds_pos(s_pos_u32 + (uint32_t)cur_si * (uint32_t)sizeof(T4), (T)0);
+            if (!valid) pi = make4<T>((T)-1.0e6, (T)-1.0e6, (T)-1.0e6, (T)0);  // idle lane group: far from the dummy atom its zero words point at
             if (!UNIFORM) {
-                T2 t = s_lj[cur.si];
+                T2 t = lds_pair(s_lj_u32 + (uint32_t)cur_si * (uint32_t)sizeof(T2), (T)0);
                 lj_s_i = t.x;
                 lj_e_i = t.y;
             }
@@ -365,7 +387,11 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
             axx = make_float2(0.f, 0.f); ayy = axx; azz = axx;
 #endif
             // main list: groups of 32 entries; each of the 8 lanes owns 4 entries (one 8-byte word) per group
-            const int n_groups = (cur.n_main + 31) >> 5;
+            const int n_groups = (cur_n_main + 31) >> 5;
+            // the four atoms of the quad run the same number of group iterations (the longest row's); shorter rows feed zero
+            // words, i.e. the dummy atom, so the loop control is warp-uniform
+            int gmax = max(n_groups, __shfl_xor_sync(0xffffffffu, n_groups, 8));
+            gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16));
             const uint2* lp2 = reinterpret_cast<const uint2*>(list + (size_t)slot * g.stride) + l;
             // second half of this quad's first batch
             uint2 wb[LIST_HALF];
@@ -376,23 +402,23 @@ __global__ void __launch_bounds__(FORCE_THREADS, (sizeof(T) == 8) ? 1 : 2)
             r = lookup(cur.seq + nbuf - 1, true, nxt);
 #pragma unroll
             for (int u = 0; u < LIST_HALF; u++)
-                if (u < n_groups) eval4(wa[u]);
+                if (u < gmax) eval4(wa[u]);
             if (r == 1) request_first(nxt);
 #pragma unroll
             for (int u = 0; u < LIST_HALF; u++)
-                if (LIST_HALF + u < n_groups) eval4(wb[u]);
+                if (LIST_HALF + u < gmax) eval4(wb[u]);
             // rows longer than one batch
-            for (int g0 = 2 * LIST_HALF; g0 < n_groups; g0 += LIST_HALF) {
+            for (int g0 = 2 * LIST_HALF; g0 < gmax; g0 += LIST_HALF) {
                 uint2 wc[LIST_HALF];
 #pragma unroll
                 for (int u = 0; u < LIST_HALF; u++)
                     wc[u] = (g0 + u < n_groups) ? ldg_stream_u2(lp2 + (size_t)(g0 + u) * 8) : make_uint2(0u, 0u);
 #pragma unroll
                 for (int u = 0; u < LIST_HALF; u++)
-                    if (g0 + u < n_groups) eval4(wc[u]);
+                    if (g0 + u < gmax) eval4(wc[u]);
             }
             // special (1-4) pairs
-            for (int m = l; m < cur.n_spec; m += 8) eval((int)slist[(size_t)slot * g.sstride + m], std::true_type{});
+            for (int m = l; m < cur_n_spec; m += 8) eval((int)slist[(size_t)slot * g.sstride + m], std::true_type{});
 #if MB_USE_F32X2
             if constexpr (std::is_same<T, float>::value) {
                 fx += axx.x + axx.y;

@@ -15,6 +15,12 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session")
-def golden_6mrr():
+def _golden_6mrr_file():
     import numpy as np
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "6mrr.npz")))
+
+
+@pytest.fixture
+def golden_6mrr(_golden_6mrr_file):
+    # fresh copies for every test: simulate() updates coords / velocities in place, and a System keeps references to its inputs
+    return {k: v.copy() for k, v in _golden_6mrr_file.items()}
