@@ -146,8 +146,11 @@ def ncu_traffic(workload_name: str):
 
 
 # ----------------------------------------------------------------------------------------------------
-def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32):
-    """Molly-algorithm CPU restatement (oracle): list every 10 steps with rc + 0.2 nm, all host threads."""
+def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32, r_list=None):
+    """Molly-algorithm CPU restatement (oracle): threaded cell list every 10 steps (the reference's find_neighbors policy,
+    src/neighbors.jl:671) with the GPU arm's list radius, threaded pair loop, all host threads."""
+    if r_list is None:
+        r_list = rc + (0.12 if "golden" in sd else 0.1)
     from oracle import oracle as o
     if "golden" in sd:  # 6mrr: pairwise in C (threaded), bonded terms in numpy, f64
         try:
@@ -157,7 +160,7 @@ def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32):
             pass
         t0 = time.perf_counter()
         H.oracle_vv_with_bonded(sd["golden"], sd["coords"].astype(np.float64), sd["velocities"].astype(np.float64), dt, steps,
-                                r_list=rc + 0.2, nl_every=10)
+                                r_list=r_list, nl_every=10)
         t = time.perf_counter() - t0
         return steps / t, o.max_threads(), t
     orc = H.make_oracle(sd, ointers, dtype=dtype)
@@ -175,9 +178,9 @@ def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32):
     for nt in sorted(cands):
         x, v = x0, v0
         if warmup > 0:
-            x, v, _ = orc.simulate_vv(x, v, dt, warmup, remove_cm_every=1, r_list=rc + 0.2, nl_every=10, n_threads=nt)
+            x, v, _ = orc.simulate_vv(x, v, dt, warmup, remove_cm_every=1, r_list=r_list, nl_every=10, n_threads=nt)
         t0 = time.perf_counter()
-        orc.simulate_vv(x, v, dt, steps, remove_cm_every=1, r_list=rc + 0.2, nl_every=10, n_threads=nt)
+        orc.simulate_vv(x, v, dt, steps, remove_cm_every=1, r_list=r_list, nl_every=10, n_threads=nt)
         t = time.perf_counter() - t0
         if best is None or steps / t > best[0]:
             best = (steps / t, nt, t)
@@ -201,6 +204,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cm", action="store_true", help="diagnostic: remove_CM_motion=false")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of the spatial decomposition")
+    ap.add_argument("--no-extra", action="store_true", help="only the primary workload (no `workloads` object)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -219,14 +223,14 @@ def main():
         steps = min(steps, 20 if wl == "c2" else (10 if wl == "c4" else 60))  # bounded sample ...
         steps = 10 * max(1, steps // 10)  # ... of whole neighbour-list periods (Molly's default: find_neighbors every 10 steps)
         warm = min(args.warmup if args.warmup is not None else 1, 2)
-        sps, nt, t = run_cpu(sd, ointers, dt, rc, steps, warm)
+        r_list = args.r_list if args.r_list is not None else (rc + 0.1 if wl != "c3" else rc + 0.12)
+        sps, nt, t = run_cpu(sd, ointers, dt, rc, steps, warm, r_list=r_list)
         out = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
-               "warmup": warm, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "warmup": warm, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
-               "config": {"workload": label, "n_atoms": int(sd["n"]), "dt_ps": dt, "r_cut_nm": rc},
+               "config": {"workload": label, "n_atoms": int(sd["n"]), "dt_ps": dt, "r_cut_nm": rc, "r_list_nm": r_list},
                "cpu_baseline": {"value": sps, "unit": UNIT, "cores": nt, "kind": "port",
-                                "sample": f"{steps} MD steps of the same workload (Molly CPU algorithm restated in C+OpenMP: "
-                                          f"cell list every 10 steps, r_list = rc+0.2 nm); Julia is not installed"},
+                                "sample": cpu_sample_text(steps, t, r_list) + "; Julia is not installed"},
                "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "ns_per_day": sps * dt * 1e3 * 0.0864}
         print(json.dumps(out))
@@ -243,12 +247,36 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = dict(rank=rank, world=world, local_rank=local_rank, dist=dist, n_gpus=n_gpus)
+    steps = args.steps if args.steps is not None else (1000 if wl != "c4" else 300)
+    warmup = max(args.warmup if args.warmup is not None else 100, 3)
+    out = run_ours(wl, args, ctx, steps, warmup, with_cpu=not args.no_cpu_baseline, with_e2e=not args.no_e2e)
+    # The other configurations BASELINE.json names ride in the same line (shorter runs): C3 = 6mrr (one GPU: the 5.7 nm box
+    # does not shard, extra GPUs run replicas), C4 = 1M-atom LJ fluid (spatially decomposed like C2 when N > 1).
+    if args.workload is None and not args.no_extra:
+        extra = {}
+        for w2, st2, wu2 in (("c3", min(steps, 400), min(warmup, 40)), ("c4", min(steps, 120), min(warmup, 20))):
+            try:
+                extra[w2] = run_ours(w2, args, ctx, max(st2, 5), max(wu2, 3), with_cpu=False, with_e2e=not args.no_e2e, brief=True)
+            except Exception as e:  # the primary line must survive an extra workload's failure
+                extra[w2] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if rank == 0:
+            out["workloads"] = extra
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
 
+
+def run_ours(wl, args, ctx, steps, warmup, with_cpu, with_e2e, brief=False):
+    """One workload on this arm; returns the JSON fields (rank 0) or None (other ranks)."""
+    import torch
+    import mollyb200 as mb
+    rank, world, local_rank, dist, n_gpus = ctx["rank"], ctx["world"], ctx["local_rank"], ctx["dist"], ctx["n_gpus"]
+    dtype = np.float32
     sd, inters, ointers, dt, rc, label = workload(wl, dtype)
     n = int(sd["n"])
     r_list = args.r_list if args.r_list is not None else (rc + 0.1 if wl != "c3" else rc + 0.12)
-    steps = args.steps if args.steps is not None else (1000 if wl != "c4" else 300)
-    warmup = max(args.warmup if args.warmup is not None else 100, 3)
 
     atoms = mb.atoms_from_arrays(sd["mass"], sd["charge"], sd["sigma"], sd["eps"], dtype)
     nf = mb.GPUNeighborFinder(dist_cutoff=r_list, excluded_pairs=sd.get("excluded", np.zeros((0, 2), np.int32)) + 1,
@@ -262,9 +290,10 @@ def main():
     sysm.engine()
     if any(args.brick) or args.lanes:
         sysm.set_launch_config(tuple(args.brick), args.lanes)
-    decomposed = world > 1 and not args.replicas
+    # C3's 5.7 nm box is smaller than 2.5 r_list per slab for any N > 1: replicas only
+    decomposed = world > 1 and not args.replicas and wl != "c3"
     if decomposed:
-        # spatial decomposition: z-slabs, NCCL halo exchange inside the library; torch.distributed only ships the id
+        # spatial decomposition: z-slabs, halo exchange inside the library; torch.distributed only ships the id
         uid = [mb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         mb.comm_init(sysm, uid[0], rank, world)
@@ -276,6 +305,13 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
     # warm-up (also builds the neighbour structure and derives capacities)
     mb.simulate(sysm, sim, warmup, rng=rng)
@@ -290,15 +326,12 @@ def main():
     mb.simulate(sysm, sim, steps, init_step=warmup, rng=rng)
     ev1.record()
     barrier()
-    t_ms = ev0.elapsed_time(ev1)
+    t_ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if rank == 0 else None
     st1 = sysm.stats()
-    if dist is not None:
-        tt = torch.tensor([t_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_ms = float(tt.item())
-    # decomposed: all ranks advance ONE system (strong scaling); replicas: every rank advances its own copy
-    value = (1 if decomposed or world == 1 else world) * steps / (t_ms * 1e-3)
+    # decomposed: all ranks advance ONE system; replicas: every rank advances its own copy
+    mult = 1 if decomposed or world == 1 else world
+    value = mult * steps / (t_ms * 1e-3)
     launches = st1["kernel_launches"] - st0["kernel_launches"]
 
     # ---- stage timers (separate short run so the event records do not perturb the number above)
@@ -307,17 +340,17 @@ def main():
     mb.simulate(sysm, sim, prof_steps, init_step=warmup + steps, rng=rng)
     stp = sysm.stats()
     sysm.set_profiling(False)
-    force_us = 1e3 * stp["force_ms"] / max(stp["force_launches"], 1)
-    vv_us = 1e3 * stp["vv_ms"] / max(stp["vv_launches"], 1)
+    force_us = max_over_ranks(1e3 * stp["force_ms"] / max(stp["force_launches"], 1))  # slowest rank's kernel
+    vv_us = max_over_ranks(1e3 * stp["vv_ms"] / max(stp["vv_launches"], 1))
     rebuilds_prof = stp["n_rebuilds"] - st1["n_rebuilds"]
     # stream mode enqueues the gated rebuild pipeline every step (2-3 us no-op kernels unless the flag is set), so this
-    # total is an upper bound of the real rebuild cost; profiles/r01_launches_*.md has the per-kernel numbers
+    # total is an upper bound of the real rebuild cost; profiles/r02_launches_*.md has the per-kernel numbers
     rebuild_total_ms = stp["rebuild_ms"]
 
     # ---- e2e through the C ABI with host (pinned) buffers
     e2e = None
-    if not args.no_e2e:
-        spc = args.md_steps_per_call
+    if with_e2e:
+        spc = min(args.md_steps_per_call, max(steps, 5))
         hx = torch.empty((n, 3), dtype=torch.float32).pin_memory()
         hv = torch.empty((n, 3), dtype=torch.float32).pin_memory()
         hx.copy_(xs.cpu())
@@ -333,7 +366,7 @@ def main():
             dist.broadcast_object_list(uid, src=0)
             mb.comm_init(hsys, uid[0], rank, world)
         ncalls = max(3, steps // spc)
-        mb.simulate(hsys, sim, spc, rng=rng)  # warm-up call (first build)
+        mb.simulate(hsys, sim, spc, rng=rng)  # warm-up calls (first build)
         mb.simulate(hsys, sim, spc, init_step=spc, rng=rng)
         mb.simulate(hsys, sim, spc, init_step=2 * spc, rng=rng)
         barrier()
@@ -341,51 +374,51 @@ def main():
         for c in range(ncalls):
             mb.simulate(hsys, sim, spc, init_step=(3 + c) * spc, rng=rng)  # H2D + spc steps + D2H, synchronous
         torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
-        if dist is not None:
-            tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_e2e = float(tt.item())
-        e2e = {"value": (1 if decomposed or world == 1 else world) * ncalls * spc / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 3 * 4,
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": mult * ncalls * spc / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 3 * 4,
                "d2h_bytes_per_step": 2 * n * 3 * 4, "md_steps_per_call": spc, "calls": ncalls,
                "note": "one 'step' of the e2e region = one simulate!-style call of md_steps_per_call MD steps with host "
                        "coords+velocities uploaded and downloaded inside the timed region"}
         hsys.close()
 
-    # ---- CPU baseline on rank 0 (bounded sample)
+    # ---- CPU baseline on rank 0 (bounded sample), same r_list as the GPU arm
     cpu = None
-    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+    if rank == 0 and n_gpus == 1 and with_cpu:
         cs = args.cpu_steps or (10 if wl == "c2" else (3 if wl == "c4" else 40))
-        sps, nt, t = run_cpu(sd, ointers, dt, rc, cs, 1)
-        cpu = {"value": sps, "unit": UNIT, "cores": nt, "kind": "port",
-               "sample": f"{cs} MD steps of the same workload in {t:.1f} s (oracle restatement of Molly's threaded CPU path, "
-                         f"cell list every 10 steps, r_list = rc+0.2 nm)"}
+        sps, nt, t = run_cpu(sd, ointers, dt, rc, cs, 1, r_list=r_list)
+        cpu = {"value": sps, "unit": UNIT, "cores": nt, "kind": "port", "sample": cpu_sample_text(cs, t, r_list)}
 
+    out = None
     if rank == 0:
         peak, peak_src = measured_peaks()
-        alg_bytes = 36.0 * n  # force-only call, f32
+        share = world if decomposed else 1          # a decomposed rank's kernel covers 1/world of the atoms and pairs
+        alg_bytes = 36.0 * n / share                # force-only call, f32, per launch of the timed kernel
+        step_bytes = 140.0 * n / share              # whole step: K1 64 + force 36 + K2 40 B/atom
         achieved = alg_bytes / (force_us * 1e-6) / 1e9 if force_us > 0 else None
+        step_gbs = step_bytes / (t_ms / steps * 1e-3) / 1e9
         pairs_in_cut = {"c2": 1.955e7, "c4": 7.64e7, "c3": 2.63e6}[wl]
         flop_per_pair = 42.0 if wl != "c3" else 50.0
         fp32_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None
-        fp32_ach = pairs_in_cut * flop_per_pair / (force_us * 1e-6) / 1e12 if force_us > 0 else None
+        fp32_ach = (pairs_in_cut / share) * flop_per_pair / (force_us * 1e-6) / 1e12 if force_us > 0 else None
+        par = ("single GPU" if world == 1 else (
+            f"spatial decomposition: {world} z-slabs; per step: "
+            + ("halo positions stored into the neighbours' extended arrays over NVLink peer memory by the drift kernel, "
+               "24-byte all-to-all of sum(m v) by the kick kernel" if st1.get("peer_transport")
+               else "NCCL send/recv halo exchange + 24-byte all-reduce")
+            + f"; rebuild interval {st1.get('reserved_', 0)} steps (adapted from displacements)"
+            if decomposed else f"{world} independent replicas (one per GPU)"))
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
-            "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "strong" if decomposed else "weak",
-            "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "ms_per_step": t_ms / steps, "higher_is_better": True,
+            # fixed-size systems: more GPUs share the same atoms (strong); replicas multiply the work (weak)
+            "scaling": "weak" if (world > 1 and not decomposed) else "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": label, "n_atoms": n, "dt_ps": dt, "r_cut_nm": rc, "r_list_nm": r_list,
                        "rebuild_policy": "displacement-triggered" if args.rebuild_every == 0 else f"every {args.rebuild_every}",
-                       "parallelism": "single GPU" if world == 1 else (
-                           f"spatial decomposition: {world} z-slabs; per step: "
-                           + ("halo positions stored into the neighbours' arrays over NVLink peer memory by the drift kernel, "
-                              "24-byte all-to-all of sum(m v) by the kick kernel" if st1.get("peer_transport")
-                              else "NCCL send/recv halo exchange + 24-byte all-reduce")
-                           + f"; NCCL all-gather at rebuilds (every {st1.get('reserved_', 0)} steps, adapted from displacements)"
-                           if decomposed else f"{world} independent replicas (one per GPU)"),
+                       "parallelism": par,
                        "brick_dims": st1["brick_dims"], "list_stride": st1["list_stride"], "n_bricks": st1["n_bricks"],
                        "l2": "not flushed between steps: step k+1 consumes the state step k wrote; per-step working set = "
-                             f"{(st1['n_list_entries'] * 2 + n * 80) / 1e6:.0f} MB (neighbour list + state) vs 126 MB L2"},
+                             f"{(st1['n_list_entries'] * 2 + n * 100) / 1e6:.0f} MB (neighbour list + state) vs 126 MB L2"},
             "ns_per_day": value * dt * 1e3 * 0.0864,
             "gpu_launches": int(launches),
             "rebuilds_in_timed_region": int(st1["n_rebuilds"] - st0["n_rebuilds"]),
@@ -394,20 +427,29 @@ def main():
             "e2e": e2e,
             "roofline": {"bound": "hbm", "kernel": "brick_force_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(wl), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": force_us},
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": force_us,
+                         "per_rank_share": f"1/{share} of the atoms per launch (slowest rank's kernel time)",
+                         "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak}},
             "fp32": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak,
                      "frac": (fp32_ach / fp32_peak) if (fp32_ach and fp32_peak) else None,
-                     "convention": f"{flop_per_pair:.0f} flop per in-cutoff pair x {pairs_in_cut:.3g} pairs (SURVEY.md §8d)",
-                     "pair_interactions_per_s": pairs_in_cut * value / (1 if decomposed or world == 1 else world)},
+                     "convention": f"{flop_per_pair:.0f} flop per in-cutoff pair x {pairs_in_cut / share:.3g} pairs per rank (SURVEY.md §8d)",
+                     "pair_interactions_per_s": pairs_in_cut * value / mult},
             "stage_us": {"force": force_us, "vv_kernels_mean": vv_us,
                          "rebuild_pipeline_total_ms_stream_mode": rebuild_total_ms,
                          "rebuilds_during_profile": int(rebuilds_prof), "profile_steps": prof_steps},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        if brief:
+            for k in ("higher_is_better", "vs_baseline", "data", "cpu_baseline", "warmup"):
+                out.pop(k, None)
     sysm.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    return out
+
+
+def cpu_sample_text(steps, seconds, r_list):
+    return (f"{steps} MD steps of the same workload in {seconds:.1f} s (oracle restatement of Molly's threaded CPU path: threaded "
+            f"cell-list build every 10 steps like CellListMap's parallel map_pairwise!, threaded pair loop with per-thread force "
+            f"copies; r_list = {r_list:.2f} nm as on the GPU arm)")
 
 
 if __name__ == "__main__":

@@ -47,6 +47,14 @@ struct Control {
     unsigned int call_max_disp2_bits;  // largest value any rebuild interval of the current call reached
 };
 
+// centre-of-mass velocity waiting to be subtracted by the next reader of the velocities (vv.cuh; written by K2's last CTA
+// or by the force kernel's fused second kick)
+template <typename T>
+struct CmState {
+    T v[3];
+    int valid;
+};
+
 struct BrickHdr {
     int halo_count;  // staged atoms incl. dummy + alignment pads
     int i_count;     // atoms owned by the brick
@@ -299,15 +307,19 @@ __device__ __forceinline__ typename VT<T>::T4 image_of(const double Ld[3], typen
 }
 // store position p of slot s into an extended array (this rank's or a peer's): the atom's own entry and its ghost copies
 template <typename T>
-__device__ __forceinline__ void ext_store(const ExtMap<T>& m, int s, typename VT<T>::T4 p, typename VT<T>::T4* __restrict__ dst) {
-    dst[m.ext_of[s]] = p;
-    const unsigned int gp = m.gptr[s];
+__device__ __forceinline__ void ext_store_at(const ExtMap<T>& m, int e_own, unsigned int gp, typename VT<T>::T4 p,
+                                             typename VT<T>::T4* __restrict__ dst) {
+    dst[e_own] = p;
     const int ng = (int)(gp >> 28);
     const int2* ge = m.ghosts + (gp & 0x0fffffffu);
     for (int k = 0; k < ng; k++) {
         const int2 e = ge[k];
         dst[e.x] = image_of<T>(m.Ld, p, e.y);
     }
+}
+template <typename T>
+__device__ __forceinline__ void ext_store(const ExtMap<T>& m, int s, typename VT<T>::T4 p, typename VT<T>::T4* __restrict__ dst) {
+    ext_store_at<T>(m, m.ext_of[s], m.gptr[s], p, dst);
 }
 // R4e: per-atom extended index + ghost table; also fills pos4e / lj2e for the positions of the rebuild
 template <typename T>
@@ -567,11 +579,11 @@ __global__ void __launch_bounds__(256)
                        const int* __restrict__ ex_ptr, const int* __restrict__ ex_idx, const int* __restrict__ sp_ptr,
                        const int* __restrict__ sp_idx, unsigned short* __restrict__ list,
                        unsigned short* __restrict__ slist, ushort2* __restrict__ counts, int2* __restrict__ task_tab,
-                       int brick0) {
+                       int brick0, int split) {
     if (!ctl->rebuild) return;
     using T4 = typename VT<T>::T4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = blockIdx.x + brick0;
+    const int b = (int)blockIdx.x / split + brick0;  // `split` CTAs share a brick: CTA k takes the tasks k, k + split, ... of each warp
     const BrickHdr hd = hdrs[b];
     if (hd.i_count == 0 || hd.halo_count > g.halo_cap) return;
     T4* s_pos = reinterpret_cast<T4*>(smem_raw);
@@ -608,7 +620,7 @@ __global__ void __launch_bounds__(256)
 
     int my_max = 0;
     unsigned long long my_pairs = 0;
-    for (int task = wid; task < hd.i_count; task += nw) {
+    for (int task = wid * split + (int)blockIdx.x % split; task < hd.i_count; task += nw * split) {
         // locate the owned atom
         int q = 0;
         while (q + 1 < g.n_irows && s_rows[q + 1].cum <= task) q++;
@@ -672,15 +684,31 @@ __global__ void __launch_bounds__(256)
             }
             const int roff = inc - rlen;  // exclusive offset of this lane's row in the flattened range
             const int total = __shfl_sync(0xffffffffu, inc, 31);
+            // Compact the non-empty rows into lanes 0 .. nnz-1 (start index, flattened offset): the walk below then maps a
+            // flattened position to its row with one warp OR-reduction and two shuffles instead of a 5-step shuffle search.
+            const unsigned int nz = __ballot_sync(0xffffffffu, rlen > 0);
+            const int nnz = __popc(nz);
+            int src = 0;
+            {
+                unsigned int m = nz;
+                int o = lane;  // position of the (lane+1)-th set bit of nz
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) {
+                    const int cnt = __popc(m & ((1u << sh) - 1u));
+                    if (o >= cnt) { o -= cnt; m >>= sh; src += sh; }
+                }
+            }
+            const int cra = __shfl_sync(0xffffffffu, ra, src & 31);
+            const int croff_all = __shfl_sync(0xffffffffu, roff, src & 31);  // (every lane takes part in the shuffle)
+            const int croff = (lane < nnz) ? croff_all : 0x3fffffff;
+            int starts_before = 0;  // compacted rows that start before k0
             for (int k0 = 0; k0 < total; k0 += 32) {
                 const int k = k0 + lane;
-                int lo = 0;  // last row whose offset is <= k (empty rows share their successor's offset)
-#pragma unroll
-                for (int st = 16; st > 0; st >>= 1) {
-                    int v = __shfl_sync(0xffffffffu, roff, lo + st);
-                    if (v <= k) lo += st;
-                }
-                const int c = __shfl_sync(0xffffffffu, ra, lo) + (k - __shfl_sync(0xffffffffu, roff, lo));
+                const unsigned int rel = (unsigned int)(croff - k0);
+                const unsigned int mask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);  // row starts inside this step
+                const int ord = starts_before + __popc(mask & (0xffffffffu >> (31 - lane))) - 1;    // last row starting at or before k
+                starts_before += __popc(mask);
+                const int c = __shfl_sync(0xffffffffu, cra, ord & 31) + (k - __shfl_sync(0xffffffffu, croff, ord & 31));
                 bool in = false, special = false;
                 if (k < total && c != si) {
                     T4 pj = s_pos[c];

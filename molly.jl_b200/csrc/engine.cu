@@ -620,7 +620,7 @@ class Engine : public EngineBase {
         max_special_host_ = 0;
         for (size_t i = 0; i + 1 < sp_ptr_.size(); i++) max_special_host_ = std::max(max_special_host_, sp_ptr_[i + 1] - sp_ptr_[i]);
         const int vvb = (int)((n_ + VV_THREADS - 1) / VV_THREADS);
-        MB_CUDA(d_partial_.ensure((size_t)std::max(vvb, 1024) * 8 * sizeof(double)));
+        MB_CUDA(d_partial_.ensure((size_t)std::max(vvb, 2048) * 8 * sizeof(double)));
         have_list_ = false;
         slots_init_ = false;
         dirty_ = false;
@@ -684,10 +684,13 @@ class Engine : public EngineBase {
                         double smem = halo * bytes_per_atom + owned * 1.3 * 8.0 + 256;
                         if (smem > smem_budget || halo * 1.1 + 96 > LIST_MAX_HALO) continue;
                         const int stages2 = (int)std::floor(cta_budget / smem);  // ring depth with two CTAs per SM
-                        const double eff = stages2 >= 2 ? 1.0 : (stages2 == 1 ? 0.8 : 0.5);
+                        double eff = stages2 >= 2 ? 1.0 : (stages2 == 1 ? 0.8 : 0.5);
+                        // a stage hands out owned/4 quads to 15 consumer warps: with fewer than ~15 quads in flight over the
+                        // ring the warps wait for the producer
+                        eff *= std::min(1.0, std::max(1, std::min(stages2, 3)) * (owned / 4.0) / 15.0);
                         double cost_b = owned * nbrs + 6.0 * halo + 2000.0;
                         double nbr = std::ceil((double)g.nc[0] / bx) * std::ceil((double)g.nc[1] / by) * std::ceil((double)g.nc[2] / bz);
-                        double t = (std::max(nbr / slots, 1.0) + 0.5) * cost_b / eff;  // + half a brick of tail
+                        double t = (std::max(nbr / slots, 1.0) + 1.5) * cost_b / eff;  // + start-up and tail: about a brick and a half
                         if (t < best_t * 0.999) { best_t = t; best[0] = bx; best[1] = by; best[2] = bz; }
                     }
         }
@@ -974,7 +977,9 @@ class Engine : public EngineBase {
     int own_nbricks() const { return build_nb_ < 0 ? g_.nbricks : build_nb_; }
     int layer_lo(int q) const { return decomp_layer_lo(q, g_.nc[2], nranks_); }
     // slot ranges and halo segments follow from the cell layer offsets of the current sort (host copy)
+    int decomposed_interval() const { return rebuild_every_ > 0 ? rebuild_every_ : auto_every_; }
     int update_ownership() {
+        own_valid_ = true;
         const int ncz = g_.nc[2], per_layer = g_.nc[0] * g_.nc[1];
         layer_start_.resize(ncz + 1);
         MB_CUDA(d_layer_start_.ensure((size_t)(ncz + 1) * sizeof(int)));
@@ -1012,21 +1017,18 @@ class Engine : public EngineBase {
     // The interval for the NEXT call is derived from the largest displacement any interval of this call reached:
     // n_next = 0.8 * n * (skin/2) / d_max, agreed between ranks with one max-all-reduce. Violations are still counted.
     int adapt_interval() {
-        unsigned int* bits = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ctl_.p) + offsetof(Control, max_disp2_bits));
-        // the running interval counts too: take max(max_disp2_bits, call_max_disp2_bits) on the device side by reading both
-        unsigned int h[2];
-        MB_CUDA(cudaMemcpyAsync(h, bits, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
-        MB_CUDA(cudaStreamSynchronize(stream_));
-        float d2;
-        unsigned int mx = std::max(h[0], h[1]);
-        memcpy(&d2, &mx, sizeof(float));
+        // largest displacement any rebuild interval of this call reached (device) -> max over ranks -> host; the only host
+        // wait is the one the end of the call has anyway
         float* dbuf = reinterpret_cast<float*>(d_mom_.as<double>() + 7);
-        MB_CUDA(cudaMemcpyAsync(dbuf, &d2, sizeof(float), cudaMemcpyHostToDevice, stream_));
+        max_disp_kernel<<<1, 1, 0, stream_>>>(d_ctl_.as<Control>(), dbuf);
+        launches_++;
         MB_NCCL(g_nccl.AllReduce(dbuf, dbuf, 1, (ncclDataType_t)7 /* ncclFloat32 */, (ncclRedOp_t)2 /* ncclMax */, comm_, stream_));
+        float d2 = 0.f;
         MB_CUDA(cudaMemcpyAsync(&d2, dbuf, sizeof(float), cudaMemcpyDeviceToHost, stream_));
         MB_CUDA(cudaStreamSynchronize(stream_));
         if (d2 > 0.f && skin_ > 0) {
-            double n_next = 0.8 * auto_every_ * (0.5 * skin_) / std::sqrt((double)d2);
+            // d2 was reached within adapt_span_ steps of a rebuild; displacements grow at most linearly in time
+            double n_next = 0.8 * std::max(adapt_span_, 1) * (0.5 * skin_) / std::sqrt((double)d2);
             auto_every_ = (int)std::min(400.0, std::max(5.0, std::floor(n_next)));
         }
         return MB_OK;
@@ -1236,13 +1238,15 @@ class Engine : public EngineBase {
         const bool has_ex = !ex_ptr_.empty() || !sp_ptr_.empty();
         auto go = [&](auto kern) -> int {
             MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<own_nbricks(), 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
+            // few bricks (small systems, narrow slabs): several CTAs share a brick's atoms so that the SMs are filled
+            const int split = std::max(1, std::min(4, (4 * sm_count_ + own_nbricks() - 1) / std::max(own_nbricks(), 1)));
+            kern<<<own_nbricks() * split, 256, smem, stream_>>>(d_ctl_.as<Control>(), g_, d_hdrs_.as<BrickHdr>(), d_runs_.as<Run>(),
                                                      d_irows_.as<IRow>(), d_hcs_.as<ushort2>(), d_pos4e_.as<T4>(), d_orig_e_.as<int>(),
                                                      ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), sp_idx_dev(),
                                                      count_only ? nullptr : d_list_.as<unsigned short>(),
                                                      count_only ? nullptr : d_slist_.as<unsigned short>(),
                                                      count_only ? nullptr : d_counts_.as<ushort2>(),
-                                                     count_only ? nullptr : d_task_tab_.as<int2>(), own_brick0());
+                                                     count_only ? nullptr : d_task_tab_.as<int2>(), own_brick0(), split);
             return MB_OK;
         };
         if (count_only) { if (has_ex) MB_TRY(go(build_lists_kernel<T, true, true>)); else MB_TRY(go(build_lists_kernel<T, true, false>)); }
@@ -1315,6 +1319,7 @@ class Engine : public EngineBase {
     int first_build(const T* coords_dev) {
         const int nb = (int)((n_ + 255) / 256);
         build_nb_ = -1;  // lists for every brick (capacities are global; mb_forces evaluates the whole box)
+        own_valid_ = false;
         init_slots_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, coords_dev, d_charge_in_.as<T>(), d_ljp_in_.as<T2>(),
                                                       d_mass_in_.as<T>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(), d_lj2_.as<T2>(),
                                                       d_orig_.as<int>(), d_inv_orig_.as<int>(), d_mass_.as<T>(), d_xref4_.as<T4>());
@@ -1382,7 +1387,10 @@ class Engine : public EngineBase {
             have_list_ = true;
             geom_version_++;
             set_l2_persistence();
-            if (decomposed()) MB_TRY(update_ownership());
+            if (decomposed()) {
+                MB_TRY(update_ownership());
+                since_rebuild_ = 0;
+            }
             return MB_OK;
         }
         return set_error(MB_ERR_CAPACITY, "could not find a brick size that fits in shared memory");
@@ -1502,10 +1510,21 @@ class Engine : public EngineBase {
                                                   d_pos4_.as<T4>(), d_vel4_.as<T4>(), &d_ctl_.as<Control>()->rebuild);
         launches_++;
         if (decomposed()) {
-            // every rank holds the full state here; rebuild unconditionally so that ownership is fresh
-            MB_TRY(set_flag_rebuild());
-            MB_TRY(enqueue_rebuild(true, false));
-            MB_TRY(update_ownership());
+            // Every rank holds the full state here. The lists of the previous call stay valid until an atom has moved more
+            // than skin/2 from its position at the last rebuild (ingest_kernel just checked that on identical data on every
+            // rank) or the rebuild interval has run out; the host needs the answer because ownership follows from the sort.
+            int flag = 0;
+            MB_CUDA(cudaMemcpyAsync(&flag, &d_ctl_.as<Control>()->rebuild, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            MB_CUDA(cudaStreamSynchronize(stream_));
+            if (flag || !own_valid_ || since_rebuild_ >= decomposed_interval()) {
+                if (own_valid_) { build_b0_ = own_b0_; build_nb_ = own_nb_; }  // lists only for the owned slab
+                MB_TRY(set_flag_rebuild());
+                MB_TRY(enqueue_rebuild(true, false));
+                MB_TRY(update_ownership());
+                since_rebuild_ = 0;
+            } else {
+                MB_TRY(ext_fill(0, (int)n_));
+            }
             return MB_OK;
         }
         MB_TRY(enqueue_rebuild(true, false));
@@ -1627,7 +1646,7 @@ class Engine : public EngineBase {
         const bool dec = decomposed() && path_ == 1;
         const int s0 = dec ? own_s0_ : 0, n_own = dec ? own_n_ : (int)n_;
         const int nb = std::max(1, (n_own + 255) / 256);
-        const int vvb = std::max(1, std::min((n_own + VV_THREADS - 1) / VV_THREADS, 4 * sm_count_));  // grid-stride: <= 592 partials
+        const int vvb = std::max(1, std::min((n_own + VV_THREADS - 1) / VV_THREADS, 8 * sm_count_));  // grid-stride: <= 1184 partials
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
         // decomposed run over peer memory (peer.cuh): K1 mirrors the boundary slots into the neighbours while it drifts
@@ -1644,7 +1663,7 @@ class Engine : public EngineBase {
             cm_deferred_epoch_ = 0;
         }
         prof_.begin(Prof::VV);
-        vv_kick_drift_kernel<T><<<std::min(nb, 4 * sm_count_), 256, 0, stream_>>>(
+        vv_kick_drift_kernel<T><<<std::min(nb, 8 * sm_count_), 256, 0, stream_>>>(  // one atom per thread up to 8 resident CTAs per SM
             s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
             c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0, push, ext_map());
         prof_.end(Prof::VV);
@@ -1677,6 +1696,7 @@ class Engine : public EngineBase {
                 // neighbour rebuild on a decomposed box: replicate positions and velocities, rebuild (identical sort on every
                 // rank, lists only for the owned slab), then refresh the slot ranges and halo segments
                 MB_TRY(allgather_state());
+                MB_TRY(set_flag_rebuild());
                 MB_TRY(enqueue_rebuild(true, false));
                 MB_TRY(update_ownership());
             } else if (p2p_halo) {
@@ -1689,7 +1709,7 @@ class Engine : public EngineBase {
         }
         const int s0b = dec ? own_s0_ : 0, n_ownb = dec ? own_n_ : (int)n_;  // ownership may have changed in the rebuild
         const int nb2 = std::max(1, (n_ownb + 255) / 256);
-        const int vvb2 = std::max(1, std::min((n_ownb + VV_THREADS - 1) / VV_THREADS, 4 * sm_count_));
+        const int vvb2 = std::max(1, std::min((n_ownb + VV_THREADS - 1) / VV_THREADS, 8 * sm_count_));
         if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
         else MB_TRY(launch_force(false, dec));
         MB_TRY(launch_bonded(false));
@@ -1792,7 +1812,7 @@ class Engine : public EngineBase {
         MB_TRY(view_in(coords, 3 * (size_t)n_, d_stage_a_, &xc));
         MB_TRY(view_in(vels, 3 * (size_t)n_, d_stage_c_, &vc));
         const int nb = (int)((n_ + 255) / 256);
-        const int vvb = std::min((int)((n_ + VV_THREADS - 1) / VV_THREADS), 4 * sm_count_);
+        const int vvb = std::min((int)((n_ + VV_THREADS - 1) / VV_THREADS), 8 * sm_count_);
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
         clear_cm_kernel<T><<<1, 1, 0, stream_>>>(cm);
@@ -1831,7 +1851,7 @@ class Engine : public EngineBase {
         {
             struct Tail { int rebuild_every; long long step, init_step; unsigned int rng[4]; unsigned int max_disp2_bits, call_max_disp2_bits; } t;
             static_assert(sizeof(Tail) == sizeof(Control) - offsetof(Control, rebuild_every), "Control tail layout");
-            t.rebuild_every = (decomposed() && path_ == 1 && rebuild_every_ == 0) ? auto_every_ : rebuild_every_;
+            t.rebuild_every = (decomposed() && path_ == 1) ? 0 : rebuild_every_;  // decomposed: the host counts the interval
             t.step = p->init_step;
             t.init_step = p->init_step;
             t.rng[0] = (unsigned int)p->rng_ctr1; t.rng[1] = (unsigned int)(p->rng_ctr1 >> 32);
@@ -1843,6 +1863,7 @@ class Engine : public EngineBase {
             MB_CUDA(cudaStreamSynchronize(stream_));  // t is a local
         }
         cm_deferred_epoch_ = 0;
+        adapt_span_ = since_rebuild_;
         bool cm_pending = false;  // host mirror of cm->valid
         if (p->init_step == 0 && p->remove_cm_every != 0) {
             // remove_CM_motion! before the first force evaluation (simulators.jl:563): zero-length kick
@@ -1895,8 +1916,15 @@ class Engine : public EngineBase {
                 const int64_t step_n = p->init_step + k;
                 const int do_cm = (p->remove_cm_every != 0 && step_n % p->remove_cm_every == 0) ? 1 : 0;
                 const bool clear_after_k1 = cm_pending && !do_cm;  // K1 consumed v_cm; nothing overwrites it this step
-                const int every = (dec && rebuild_every_ == 0) ? auto_every_ : rebuild_every_;  // decomposed: fixed interval, adapted per call
-                const bool hint = every > 0 && k > 1 && (step_n - 1) % every == 0;
+                // decomposed: fixed interval counted on the host (identical on every rank), adapted per call from the displacements
+                bool hint;
+                if (dec) {
+                    hint = since_rebuild_ >= decomposed_interval();
+                    since_rebuild_ = hint ? 1 : since_rebuild_ + 1;
+                    adapt_span_ = std::max(adapt_span_, since_rebuild_);
+                } else {
+                    hint = rebuild_every_ > 0 && k > 1 && (step_n - 1) % rebuild_every_ == 0;
+                }
                 MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint, /*defer_cm=*/k < p->n_steps));
                 cm_pending = (do_cm != 0) && !c.thermostat;
                 n_steps_++;
@@ -2078,6 +2106,9 @@ class Engine : public EngineBase {
     ncclComm_t comm_ = nullptr;
     int rank_ = 0, nranks_ = 1;
     int own_b0_ = 0, own_nb_ = 0;        // this rank's bricks (static for a geometry)
+    bool own_valid_ = false;             // ownership derived from the current sort
+    int since_rebuild_ = 0;              // MD steps since the last rebuild of a decomposed run (host count, same on every rank)
+    int adapt_span_ = 0;                 // longest such count within the current call
     int build_b0_ = 0, build_nb_ = -1;   // brick range the list builder covers (-1 = all)
     int own_s0_ = 0, own_n_ = 0;         // this rank's slots (changes at every rebuild)
     int auto_every_ = 20;                // rebuild interval of decomposed runs when the policy is displacement-triggered

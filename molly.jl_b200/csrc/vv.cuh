@@ -13,11 +13,6 @@
 
 namespace mb {
 
-template <typename T>
-struct CmState {
-    T v[3];
-    int valid;
-};
 
 // ---- first-touch initialisation: slot order = original order -------------------------------------
 template <typename T>
@@ -170,6 +165,10 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
         const typename VT<T>::T4 f = f4[s];
         typename VT<T>::T4 p = pos4[s];
         const typename VT<T>::T4 r = xref4[s];
+        // map into the extended array, requested together with the state so that no load waits behind the arithmetic
+        int e_own = 0;
+        unsigned int e_gp = 0;
+        if (ext.pos4e) { e_own = ext.ext_of[s]; e_gp = ext.gptr[s]; }
         if (cmv) { v.x -= cx; v.y -= cy; v.z -= cz; }
         const T a = v.w * dt_half;  // (1/m) dt/2
         v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
@@ -178,9 +177,9 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
         pos4[s] = p;
         if (ext.pos4e) {
             // extended (ghost-padded) array the force kernel stages from: own entry + periodic-image copies
-            ext_store<T>(ext, s, p, ext.pos4e);
+            ext_store_at<T>(ext, e_own, e_gp, p, ext.pos4e);
             for (int q = 0; q < push.n_seg; q++)  // halo exchange fused into the drift: mirror boundary slots into the peers
-                if ((unsigned int)(s - push.start[q]) < (unsigned int)push.count[q]) ext_store<T>(ext, s, p, push.dst[q]);
+                if ((unsigned int)(s - push.start[q]) < (unsigned int)push.count[q]) ext_store_at<T>(ext, e_own, e_gp, p, push.dst[q]);
         }
         const T dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
         const T d2 = dx * dx + dy * dy + dz * dz;
@@ -303,6 +302,12 @@ __global__ void __launch_bounds__(VV_THREADS)
             }
         }
     }
+}
+
+// sqrt-free displacement summary of a call for the interval adaptation of decomposed runs: max(current interval, earlier ones)
+__global__ void max_disp_kernel(const Control* __restrict__ ctl, float* __restrict__ out) {
+    const unsigned int m = max(ctl->max_disp2_bits, ctl->call_max_disp2_bits);
+    out[0] = __uint_as_float(m);
 }
 
 template <typename T>
