@@ -337,6 +337,7 @@ def run_ours(wl, args, ctx, steps, warmup, with_cpu, with_e2e, brief=False):
     # ---- stage timers (separate short run so the event records do not perturb the number above)
     prof_steps = min(200, steps)
     sysm.set_profiling(True)
+    barrier()  # decomposed runs: a late rank would show up as waiting time inside its neighbours' kernels
     mb.simulate(sysm, sim, prof_steps, init_step=warmup + steps, rng=rng)
     stp = sysm.stats()
     sysm.set_profiling(False)

@@ -643,6 +643,16 @@ __global__ void __launch_bounds__(256)
         int sp_a = sp_ptr ? sp_ptr[oi] : 0, sp_n = sp_ptr ? sp_ptr[oi + 1] - sp_a : 0;
         int my_ex = (lane < ex_n) ? ex_idx[ex_a + lane] : -2;
         int my_sp = (lane < sp_n) ? sp_idx[sp_a + lane] : -2;
+        // Partners are bonded neighbours, so their original indices lie within a short span of oi. A step of 32 candidates
+        // that holds no atom inside that span skips both partner loops (most steps: the partner lists are checked for a
+        // few candidates per atom only).
+        int span_lo = 0x7fffffff, span_hi = -1;
+        if (HAS_EX) {
+            for (int kk = lane; kk < ex_n; kk += 32) { const int v = ex_idx[ex_a + kk]; span_lo = min(span_lo, v); span_hi = max(span_hi, v); }
+            for (int kk = lane; kk < sp_n; kk += 32) { const int v = sp_idx[sp_a + kk]; span_lo = min(span_lo, v); span_hi = max(span_hi, v); }
+            span_lo = __reduce_min_sync(0xffffffffu, span_lo);
+            span_hi = __reduce_max_sync(0xffffffffu, span_hi);
+        }
         int count = 0, scount = 0;
         unsigned short* my_list = list + (size_t)slot * g.stride;
         unsigned short* my_slist = slist + (size_t)slot * g.sstride;
@@ -717,8 +727,9 @@ __global__ void __launch_bounds__(256)
                     in = d2 <= g.rlist2;
                 }
                 int oj = (HAS_EX && in) ? s_orig[c] : -1;
+                const bool near_partner = HAS_EX && __any_sync(0xffffffffu, in && oj >= span_lo && oj <= span_hi);
                 // exclusions (warp-uniform loops over the partner lists)
-                if (HAS_EX && ex_n > 0) {
+                if (HAS_EX && near_partner && ex_n > 0) {
                     int nn = min(ex_n, 32);
                     for (int kk = 0; kk < nn; kk++) {
                         int v = __shfl_sync(0xffffffffu, my_ex, kk);
@@ -727,7 +738,7 @@ __global__ void __launch_bounds__(256)
                     for (int kk = 32; kk < ex_n; kk++)
                         if (ex_idx[ex_a + kk] == oj) in = false;
                 }
-                if (HAS_EX && sp_n > 0) {
+                if (HAS_EX && near_partner && sp_n > 0) {
                     int nn = min(sp_n, 32);
                     for (int kk = 0; kk < nn; kk++) {
                         int v = __shfl_sync(0xffffffffu, my_sp, kk);

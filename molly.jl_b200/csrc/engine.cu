@@ -1663,9 +1663,11 @@ class Engine : public EngineBase {
             cm_deferred_epoch_ = 0;
         }
         prof_.begin(Prof::VV);
-        vv_kick_drift_kernel<T><<<std::min(nb, 8 * sm_count_), 256, 0, stream_>>>(  // one atom per thread up to 8 resident CTAs per SM
+        const Thermo<T> th = thermo_in_k1(c);
+        auto k1 = th.on ? vv_kick_drift_kernel<T, true> : vv_kick_drift_kernel<T, false>;
+        k1<<<std::min(nb, 8 * sm_count_), 256, 0, stream_>>>(  // one atom per thread up to 8 resident CTAs per SM
             s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
-            c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0, push, ext_map());
+            c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0, push, ext_map(), th);
         prof_.end(Prof::VV);
         launches_++;
         if (clear_cm_after_k1) {
@@ -1735,12 +1737,27 @@ class Engine : public EngineBase {
             cm_from_sum_kernel<T><<<1, 1, 0, stream_>>>(d_mom_.as<double>() + 4, c.inv_mass, cm);
             launches_++;
         }
-        if (c.thermostat) {
+        if (c.thermostat && !thermo_in_k1(c).on) {
             andersen_kernel<T><<<nb2, 256, 0, stream_>>>(s0b, n_ownb, (int)n_, c.kT, c.prob, d_orig_.as<int>(), d_mass_.as<T>(), d_vel4_.as<T4>(), cm, ctl);
             launches_++;
         }
         MB_CUDA(cudaGetLastError());
         return MB_OK;
+    }
+    // single-GPU step loop: the thermostat of step n runs at the top of step n+1's drift kernel; the last step of a call is
+    // closed by the standalone kernel (simulate_vv)
+    Thermo<T> thermo_in_k1(const StepCfg& c) const {
+        Thermo<T> th;
+        memset(&th, 0, sizeof(th));
+        if (c.thermostat && !decomposed()) {
+            th.on = 1;
+            th.n = (int)n_;
+            th.kT = c.kT;
+            th.prob = c.prob;
+            th.orig = d_orig_.as<int>();
+            th.mass = d_mass_.as<T>();
+        }
+        return th;
     }
 
     struct GraphKey {
@@ -1926,9 +1943,14 @@ class Engine : public EngineBase {
                     hint = rebuild_every_ > 0 && k > 1 && (step_n - 1) % rebuild_every_ == 0;
                 }
                 MB_TRY(enqueue_step(c, do_cm, clear_after_k1, false, 0, nullptr, nullptr, hint, /*defer_cm=*/k < p->n_steps));
-                cm_pending = (do_cm != 0) && !c.thermostat;
+                cm_pending = (do_cm != 0) && !(c.thermostat && dec);  // (the standalone thermostat kernel consumes v_cm)
                 n_steps_++;
             }
+        }
+        if (c.thermostat && !dec && p->n_steps > 0) {
+            // the thermostat of the last step (the earlier ones ran inside the next step's drift kernel)
+            andersen_kernel<T><<<nb, 256, 0, stream_>>>(0, (int)n_, (int)n_, c.kT, c.prob, d_orig_.as<int>(), d_mass_.as<T>(), d_vel4_.as<T4>(), cm, ctl);
+            launches_++;
         }
         if (dec) {
             MB_TRY(allgather_state());  // every rank returns the whole system

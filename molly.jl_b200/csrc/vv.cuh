@@ -123,16 +123,59 @@ __global__ void scatter_forces_kernel(int n, const typename VT<T>::T4* __restric
     fs_mat[3 * (size_t)o + 2] += f.z;
 }
 
+// ---- Andersen thermostat arithmetic (src/coupling.jl:197-212, GPU kernel src/kernels.jl:705-721) ------------------------
+// Philox4x32-10 keyed by the two rand(rng, UInt64) of the reference, counter = (original atom index, step): the draw for an
+// atom does not depend on which kernel or rank evaluates it. Statistical parity only.
+template <typename T>
+struct Thermo {
+    int on;            // apply the thermostat of the PREVIOUS step at the top of the drift kernel (step loop of one GPU)
+    int n;             // atoms in the system (second counter block)
+    T kT;
+    double prob;
+    const int* orig;
+    const T* mass;
+};
+template <typename T>
+__device__ __forceinline__ void andersen_apply(typename VT<T>::T4& v, int orig_index, int n, T m, T kT, double prob, uint32_t step_lo,
+                                               uint32_t ctr1_lo, uint32_t ctr1_hi, uint32_t key_lo, uint32_t key_hi) {
+    uint32_t c[4] = {(uint32_t)(orig_index + 1), step_lo, ctr1_lo, ctr1_hi};
+    philox4x32_10(c, key_lo, key_hi);
+    double u = ((double)c[0] * 4294967296.0 + (double)c[1]) * (1.0 / 18446744073709551616.0);
+    if (u < prob) {
+        uint32_t d[4] = {(uint32_t)(orig_index + 1 + n), step_lo, ctr1_lo, ctr1_hi};
+        philox4x32_10(d, key_lo, key_hi);
+        const double two_pi = 6.283185307179586;
+        double u1 = ((double)d[0] + 1.0) * (1.0 / 4294967296.0), u2 = (double)d[1] * (1.0 / 4294967296.0);
+        double u3 = ((double)d[2] + 1.0) * (1.0 / 4294967296.0), u4 = (double)d[3] * (1.0 / 4294967296.0);
+        double r1 = sqrt(-2.0 * log(u1)), r2 = sqrt(-2.0 * log(u3));
+        double sd = (m > (T)0) ? sqrt((double)kT / (double)m) : 0.0;
+        v.x = (T)(sd * r1 * cos(two_pi * u2));
+        v.y = (T)(sd * r1 * sin(two_pi * u2));
+        v.z = (T)(sd * r2 * cos(two_pi * u4));
+    }
+}
+
 // ---- K1: first half kick + drift + displacement check; the last CTA to finish does the step bookkeeping:
 // advance step_n, apply the fixed-interval neighbour policy (find_neighbors every n_steps, src/neighbors.jl:671) and
 // publish the rebuild decision to the CUDA graph's conditional node (when the step runs as a graph).
-template <typename T>
+// THERMO: the variant that also applies the previous step's Andersen thermostat (Philox + Box-Muller inlined) is a separate
+// instantiation so that the plain kernel keeps its register count (one atom per thread, latency-bound: occupancy matters).
+template <typename T, bool THERMO>
 __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half2, const CmState<T>* __restrict__ cm,
                                      const typename VT<T>::T4* __restrict__ f4,
                                      const typename VT<T>::T4* __restrict__ xref4, typename VT<T>::T4* __restrict__ pos4,
                                      typename VT<T>::T4* __restrict__ vel4, int* __restrict__ flag, Control* __restrict__ ctl,
-                                     cudaGraphConditionalHandle handle, int use_handle, PeerPush<T> push, ExtMap<T> ext) {
+                                     cudaGraphConditionalHandle handle, int use_handle, PeerPush<T> push, ExtMap<T> ext,
+                                     Thermo<T> th) {
     bool cmv = cm->valid != 0;
+    // thermostat of the step that just ended, folded in here (the standalone kernel would be one more launch per step):
+    // same order of operations on v - subtract the pending v_cm, resample, then this step's first kick
+    bool thermo = false;
+    uint32_t t_step = 0, t_c0 = 0, t_c1 = 0, t_k0 = 0, t_k1 = 0;
+    if (THERMO && th.on) {  // (no loads from the control block on the path without a thermostat)
+        thermo = ctl->step > ctl->init_step;
+        t_step = (uint32_t)ctl->step; t_c0 = ctl->rng[0]; t_c1 = ctl->rng[1]; t_k0 = ctl->rng[2]; t_k1 = ctl->rng[3];
+    }
     T cx = cm->v[0], cy = cm->v[1], cz = cm->v[2];
     if (push.n_peer > 0 || push.cm_nranks > 0) {  // decomposed run over peer memory (peer.cuh)
         __shared__ double s_cm[3];
@@ -170,6 +213,7 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
         unsigned int e_gp = 0;
         if (ext.pos4e) { e_own = ext.ext_of[s]; e_gp = ext.gptr[s]; }
         if (cmv) { v.x -= cx; v.y -= cy; v.z -= cz; }
+        if (THERMO && thermo) andersen_apply<T>(v, th.orig[s], th.n, th.mass[s], th.kT, th.prob, t_step, t_c0, t_c1, t_k0, t_k1);
         const T a = v.w * dt_half;  // (1/m) dt/2
         v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
         p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
@@ -361,22 +405,7 @@ __global__ void andersen_kernel(int s0, int n_own, int n, T kT, double prob, con
     if (s < s0 + n_own) {
         typename VT<T>::T4 v = vel4[s];
         if (cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
-        uint32_t c[4] = {(uint32_t)(orig[s] + 1), step_lo, ctr1_lo, ctr1_hi};
-        philox4x32_10(c, key_lo, key_hi);
-        double u = ((double)c[0] * 4294967296.0 + (double)c[1]) * (1.0 / 18446744073709551616.0);
-        if (u < prob) {
-            uint32_t d[4] = {(uint32_t)(orig[s] + 1 + n), step_lo, ctr1_lo, ctr1_hi};
-            philox4x32_10(d, key_lo, key_hi);
-            const double two_pi = 6.283185307179586;
-            double u1 = ((double)d[0] + 1.0) * (1.0 / 4294967296.0), u2 = (double)d[1] * (1.0 / 4294967296.0);
-            double u3 = ((double)d[2] + 1.0) * (1.0 / 4294967296.0), u4 = (double)d[3] * (1.0 / 4294967296.0);
-            double r1 = sqrt(-2.0 * log(u1)), r2 = sqrt(-2.0 * log(u3));
-            T m = mass[s];
-            double sd = (m > (T)0) ? sqrt((double)kT / (double)m) : 0.0;
-            v.x = (T)(sd * r1 * cos(two_pi * u2));
-            v.y = (T)(sd * r1 * sin(two_pi * u2));
-            v.z = (T)(sd * r2 * cos(two_pi * u4));
-        }
+        andersen_apply<T>(v, orig[s], n, mass[s], kT, prob, step_lo, ctr1_lo, ctr1_hi, key_lo, key_hi);
         vel4[s] = v;
     }
     // last CTA clears the pending CM state
