@@ -108,6 +108,11 @@ int mb_set_atoms_soa(mb_ctx* ctx, int64_t n, const void* mass, const void* charg
                      const void* eps);
 /* CubicBoundary side lengths (src/spatial.jl:40). */
 int mb_set_box(mb_ctx* ctx, const double side[3]);
+/* TriclinicBoundary(bv1, bv2, bv3) (src/spatial.jl:151-215): three basis vectors, row-major (bv1 = basis_vectors[0..2] along
+ * x; bv2 in the xy plane; bv3 with a positive z component), approx_images = true. Minimum image as vector() :528-534, wrap
+ * as wrap_coords :584-600. Served by the no-list kernel (the reference's triclinic tests are small systems:
+ * test/gpu_consistency.jl:287-337); specific interaction lists, PME and decomposed runs are refused for such a box. */
+int mb_set_box_triclinic(mb_ctx* ctx, const double basis_vectors[9]);
 /* sys.pairwise_inters translated to descriptors (dispatch by type in the reference). */
 int mb_set_inters(mb_ctx* ctx, int n_inters, const mb_inter_t* inters);
 /* GPUNeighborFinder sparse metadata (src/neighbors.jl:104-115, :171-195): 1-based pairs, any order,

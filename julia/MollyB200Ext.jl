@@ -109,7 +109,7 @@ const CONTEXTS = IdDict{Any, Context}()
 
 function engine_eligible(sys::System{3, <:CuArray, T}, inters) where T
     T in (Float32, Float64) || return nothing
-    sys.boundary isa CubicBoundary || return nothing
+    (sys.boundary isa CubicBoundary || sys.boundary isa TriclinicBoundary{3, <:Any, <:Any, true}) || return nothing
     length(sys.constraints) == 0 || return nothing
     isempty(sys.virtual_sites) || return nothing
     descs = map(descriptor, inters)
@@ -130,8 +130,14 @@ function context_for(sys::System{3, <:CuArray, T}, descs::Vector{MBInter}) where
         # atoms: Molly's bits layout Atom{Int32,T,T,T,T,T} is read directly from device memory
         check(ccall((:mb_set_atoms, LIB), Cint, (Ptr{Cvoid}, Int64, CuPtr{Cvoid}), h[], length(sys.atoms),
                     pointer(sys.atoms)))
-        side = Float64.(ustrip.(sys.boundary.side_lengths))
-        check(ccall((:mb_set_box, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), h[], collect(side)))
+        if sys.boundary isa TriclinicBoundary      # approx_images = true only (engine_eligible); no-list kernel
+            bv = sys.boundary.basis_vectors
+            basis = Float64[ustrip(bv[i][j]) for i in 1:3 for j in 1:3]   # row-major: bv1, bv2, bv3
+            check(ccall((:mb_set_box_triclinic, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), h[], basis))
+        else
+            side = Float64.(ustrip.(sys.boundary.side_lengths))
+            check(ccall((:mb_set_box, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), h[], collect(side)))
+        end
         if nf isa GPUNeighborFinder
             ei, ej = Array(nf.excluded_i), Array(nf.excluded_j)     # sparse 1-based lists, neighbors.jl:104-115
             si, sj = Array(nf.special_i), Array(nf.special_j)

@@ -6,7 +6,7 @@ binding and the host-side mirror of the reference interface.
 """
 from . import _capi  # noqa: F401
 from .api import *  # noqa: F401,F403
-from .api import (Atom, CubicBoundary, System, NoCutoff, DistanceCutoff, ShiftedPotentialCutoff,  # noqa: F401
+from .api import (Atom, CubicBoundary, TriclinicBoundary, System, NoCutoff, DistanceCutoff, ShiftedPotentialCutoff,  # noqa: F401
                   ShiftedForceCutoff, LennardJones, Coulomb, CoulombReactionField, CoulombEwald, GPUNeighborFinder,
                   DistanceNeighborFinder, CellListMapNeighborFinder, TreeNeighborFinder, AndersenThermostat,
                   VelocityVerlet, forces, forces_virial, potential_energy, forces_energy, find_neighbors, simulate,

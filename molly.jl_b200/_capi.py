@@ -19,7 +19,7 @@ EXPORTED = [
     "mb_forces_energy", "mb_simulate_vv", "mb_remove_cm_motion", "mb_kinetic_energy", "mb_rebuild_neighbors",
     "mb_stats", "mb_synchronize", "mb_set_capacity_scale", "mb_set_launch_config", "mb_comm_unique_id",
     "mb_comm_init", "mb_decomp_plan", "mb_set_profiling", "mb_set_specific", "mb_forces_energy_all", "mb_set_pme", "mb_pme_plan",
-    "mb_set_lj_dispersion_correction", "mb_random_velocities", "mb_kinetic_energy_tensor",
+    "mb_set_lj_dispersion_correction", "mb_random_velocities", "mb_kinetic_energy_tensor", "mb_set_box_triclinic",
 ]
 
 

@@ -85,6 +85,25 @@ class CubicBoundary:
         return np.array([self.x, self.y, self.z], np.float64)
 
 
+class TriclinicBoundary:
+    """TriclinicBoundary(bv1, bv2, bv3) — src/spatial.jl:151-215 (approx_images = true): lower-triangular basis vectors.
+    Systems in such a box run on the no-list kernel."""
+
+    def __init__(self, bv1, bv2, bv3):
+        self.basis_vectors = np.array([bv1, bv2, bv3], np.float64).reshape(3, 3)
+        bv = self.basis_vectors
+        if not (bv[0, 0] > 0 and bv[0, 1] == 0 and bv[0, 2] == 0):
+            raise ValueError("first basis vector must be along the x-axis with a positive x component")
+        if not (bv[1, 1] > 0 and bv[1, 2] == 0):
+            raise ValueError("second basis vector must be in the xy plane with a positive y component")
+        if not bv[2, 2] > 0:
+            raise ValueError("third basis vector must have a positive z component")
+
+    @property
+    def side_lengths(self):  # heights (what the engine's geometry code sees)
+        return np.array([self.basis_vectors[0, 0], self.basis_vectors[1, 1], self.basis_vectors[2, 2]], np.float64)
+
+
 @dataclass
 class NoCutoff:
     pass
@@ -372,8 +391,11 @@ class System:
     def _configure(self):
         L, ctx = self._L, self._ctx
         capi.check(L.mb_set_atoms(ctx, self.n, self.atoms.ctypes.data))
-        side = (C.c_double * 3)(*self.boundary.side_lengths)
-        capi.check(L.mb_set_box(ctx, side))
+        if isinstance(self.boundary, TriclinicBoundary):
+            capi.check(L.mb_set_box_triclinic(ctx, (C.c_double * 9)(*self.boundary.basis_vectors.ravel())))
+        else:
+            side = (C.c_double * 3)(*self.boundary.side_lengths)
+            capi.check(L.mb_set_box(ctx, side))
         descs = [it.descriptor() for it in self.pairwise_inters]
         arr = (capi.MBInter * max(1, len(descs)))(*descs)
         capi.check(L.mb_set_inters(ctx, len(descs), arr))

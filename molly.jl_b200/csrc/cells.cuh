@@ -69,6 +69,38 @@ struct IRow {
     int slot_begin, count, smem_begin, cum;
 };
 
+// TriclinicBoundary (src/spatial.jl:151-215): lower-triangular basis vectors, reciprocal heights and the projection
+// constants of wrap_coords. Served by the no-list kernel only (boxes of this kind are small systems in the reference's
+// tests); on = 0 for CubicBoundary.
+template <typename T>
+struct Tric {
+    int on;
+    T bv[3][3];
+    T rs[3];
+    T cot_bprojyz_cprojyz, cprojxy_x_over_z, cprojxy_y_over_z, cot_a_b;
+};
+// vector(c1, c2, ::TriclinicBoundary) with approx_images = true (src/spatial.jl:528-534): z, then y, then x
+template <typename T>
+__host__ __device__ inline void tric_vector(const Tric<T>& t, T& dx, T& dy, T& dz) {
+    T k = ffloor(dz * t.rs[2] + (T)0.5);
+    dx -= t.bv[2][0] * k; dy -= t.bv[2][1] * k; dz -= t.bv[2][2] * k;
+    k = ffloor(dy * t.rs[1] + (T)0.5);
+    dx -= t.bv[1][0] * k; dy -= t.bv[1][1] * k; dz -= t.bv[1][2] * k;
+    k = ffloor(dx * t.rs[0] + (T)0.5);
+    dx -= t.bv[0][0] * k; dy -= t.bv[0][1] * k; dz -= t.bv[0][2] * k;
+}
+// wrap_coords(v, ::TriclinicBoundary) (src/spatial.jl:584-600)
+template <typename T>
+__host__ __device__ inline void tric_wrap(const Tric<T>& t, T& x, T& y, T& z) {
+    T k = ffloor(z * t.rs[2]);
+    x -= t.bv[2][0] * k; y -= t.bv[2][1] * k; z -= t.bv[2][2] * k;
+    k = ffloor((y - z * t.cot_bprojyz_cprojyz) * t.rs[1]);
+    x -= t.bv[1][0] * k; y -= t.bv[1][1] * k; z -= t.bv[1][2] * k;
+    const T ddx = z * t.cprojxy_x_over_z, ddy = z * t.cprojxy_y_over_z;
+    k = ffloor((x - ddx - (y - ddy) * t.cot_a_b) * t.rs[0]);
+    x -= t.bv[0][0] * k; y -= t.bv[0][1] * k; z -= t.bv[0][2] * k;
+}
+
 template <typename T>
 struct Geom {
     T L[3], invL[3];
@@ -82,6 +114,7 @@ struct Geom {
     int task_cap;  // entries per brick of the task table (even; 0 while the capacities are being measured)
     int nce[3], necells, nerows;  // extended grid: nc + 2h cells per dimension, rows = nce[1] * nce[2]
     int ext_cap, ghost_cap;       // capacities of pos4e / the ghost table (0 while they are being measured)
+    Tric<T> tric;                 // no-list path only
     int n;        // atoms
     int align;    // atoms per 16 bytes of the lj2 array (2 for float, 1 for double)
     T rlist2;

@@ -62,8 +62,8 @@ __device__ __forceinline__ float frsqrt(float x) {
 __device__ __forceinline__ double frsqrt(double x) { return 1.0 / sqrt(x); }
 __device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double fsqrt(double x) { return sqrt(x); }
-__device__ __forceinline__ float ffloor(float x) { return floorf(x); }
-__device__ __forceinline__ double ffloor(double x) { return floor(x); }
+__host__ __device__ __forceinline__ float ffloor(float x) { return floorf(x); }
+__host__ __device__ __forceinline__ double ffloor(double x) { return floor(x); }
 __device__ __forceinline__ float frint(float x) { return rintf(x); }
 __device__ __forceinline__ double frint(double x) { return rint(x); }
 

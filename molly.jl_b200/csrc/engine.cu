@@ -291,6 +291,7 @@ class EngineBase {
     virtual int set_atoms_aos(int64_t n, const void* aos) = 0;
     virtual int set_atoms_soa(int64_t n, const void* mass, const void* charge, const void* sigma, const void* eps) = 0;
     virtual int set_box(const double side[3]) = 0;
+    virtual int set_box_triclinic(const double basis[9]) = 0;
     virtual int set_inters(int n, const mb_inter_t* in) = 0;
     virtual int set_exceptions(int64_t ne, const int32_t* ei, const int32_t* ej, int64_t ns, const int32_t* si,
                                const int32_t* sj) = 0;
@@ -385,6 +386,33 @@ class Engine : public EngineBase {
                 return set_error(MB_ERR_INVALID, "mb_set_box: side lengths must be finite and > 0 (CubicBoundary)");
             box_[d] = side[d];
         }
+        memset(&tric_, 0, sizeof(tric_));
+        dirty_ = true;
+        return MB_OK;
+    }
+    // TriclinicBoundary(bv1, bv2, bv3) (src/spatial.jl:165-215): lower-triangular basis, positive diagonal. Such systems run
+    // on the no-list kernel (minimum image :528-534, wrap :584-600); the cell-list path is for Cubic/Rectangular boxes.
+    int set_box_triclinic(const double b[9]) override {
+        if (!(b[0] > 0) || b[1] != 0 || b[2] != 0)
+            return set_error(MB_ERR_INVALID, "mb_set_box_triclinic: first basis vector must be along the x-axis with a positive x component");
+        if (!(b[4] > 0) || b[5] != 0)
+            return set_error(MB_ERR_INVALID, "mb_set_box_triclinic: second basis vector must be in the xy plane with a positive y component");
+        if (!(b[8] > 0)) return set_error(MB_ERR_INVALID, "mb_set_box_triclinic: third basis vector must have a positive z component");
+        for (int k = 0; k < 9; k++)
+            if (std::isinf(b[k]) || std::isnan(b[k])) return set_error(MB_ERR_INVALID, "mb_set_box_triclinic: infinite boundaries are not supported");
+        Tric<T> t;
+        memset(&t, 0, sizeof(t));
+        t.on = 1;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) t.bv[i][j] = (T)b[3 * i + j];
+        t.rs[0] = (T)(1.0 / b[0]); t.rs[1] = (T)(1.0 / b[4]); t.rs[2] = (T)(1.0 / b[8]);
+        const double by = b[4], bz = b[5], cy = b[7], cz = b[8];
+        t.cot_bprojyz_cprojyz = (T)std::fabs((by * cy + bz * cz) / (by * cz - bz * cy));
+        t.cprojxy_x_over_z = (T)(b[6] / std::fabs(b[8]));
+        t.cprojxy_y_over_z = (T)(b[7] / std::fabs(b[8]));
+        t.cot_a_b = (T)(b[3] / b[4]);
+        tric_ = t;
+        box_[0] = b[0]; box_[1] = b[4]; box_[2] = b[8];  // heights: volume = their product
         dirty_ = true;
         return MB_OK;
     }
@@ -504,7 +532,10 @@ class Engine : public EngineBase {
                 any_nocut_nl = true;
         }
         const double min_box = std::min(box_[0], std::min(box_[1], box_[2]));
-        path_ = (all_nl && r_list_ > 0 && min_box >= 2.5 * r_list_ && n_ >= 64) ? 1 : 0;
+        path_ = (all_nl && r_list_ > 0 && min_box >= 2.5 * r_list_ && n_ >= 64 && !tric_.on) ? 1 : 0;
+        if (tric_.on && (has_lists() || pme_on_))
+            return set_error(MB_ERR_INVALID, "TriclinicBoundary: specific interaction lists and PME are not supported by this engine");
+        if (tric_.on && decomposed()) return set_error(MB_ERR_INVALID, "TriclinicBoundary: not available in decomposed (multi-GPU) runs");
         if (path_ == 1 && max_rc > r_list_)
             return set_error(MB_ERR_INVALID, "neighbour list radius is smaller than an interaction cutoff");
         skin_ = (path_ == 1) ? (any_nocut_nl ? 0.0 : r_list_ - max_rc) : 0.0;
@@ -1456,7 +1487,7 @@ class Engine : public EngineBase {
         double* vir = pe + nblk;
         T Lx = (T)box_[0], Ly = (T)box_[1], Lz = (T)box_[2];
 #define MB_AP(SH, EN)                                                                                              \
-    allpairs_force_kernel<T, COUL, SH, EN><<<nblk, AP_THREADS, 0, stream_>>>((int)n_, P_, Lx, Ly, Lz, posq, lj2,    \
+    allpairs_force_kernel<T, COUL, SH, EN><<<nblk, AP_THREADS, 0, stream_>>>((int)n_, P_, Lx, Ly, Lz, tric_, posq, lj2, \
                                                                               ex_ptr_dev(), ex_idx_dev(), sp_ptr_dev(), \
                                                                               sp_idx_dev(), f4, pe, vir)
         prof_.begin(Prof::FORCE);
@@ -1852,6 +1883,7 @@ class Engine : public EngineBase {
             memset(&g0, 0, sizeof(g0));
             for (int d = 0; d < 3; d++) { g0.L[d] = (T)box_[d]; g0.invL[d] = (T)(1.0 / box_[d]); }
             g0.skin_half2 = std::numeric_limits<T>::infinity();
+            g0.tric = tric_;
             g_ap_ = g0;
             ingest_kernel<T><<<nb, 256, 0, stream_>>>((int)n_, g0, xc, vc, d_orig_.as<int>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(),
                                                       d_vel4_.as<T4>(), &ctl->disp);
@@ -2116,6 +2148,7 @@ class Engine : public EngineBase {
     int path_ = 0;
     PairParams<T> P_;
     Geom<T> g_, g_ap_;
+    Tric<T> tric_ = {};  // TriclinicBoundary (on = 0: cubic / rectangular box)
     Control last_ctl_;
     int64_t launches_ = 0, n_force_evals_ = 0, n_steps_ = 0, graph_step_launches_ = 0;
     Prof prof_;
@@ -2236,6 +2269,11 @@ int mb_set_atoms_soa(mb_ctx* ctx, int64_t n, const void* mass, const void* charg
     return ctx->e->set_atoms_soa(n, mass, charge, sigma, eps);
 }
 int mb_set_box(mb_ctx* ctx, const double side[3]) { MB_CTX_GUARD(ctx); return ctx->e->set_box(side); }
+int mb_set_box_triclinic(mb_ctx* ctx, const double basis_vectors[9]) {
+    MB_CTX_GUARD(ctx);
+    if (!basis_vectors) return mb::set_error(MB_ERR_INVALID, "mb_set_box_triclinic: null basis");
+    return ctx->e->set_box_triclinic(basis_vectors);
+}
 int mb_set_inters(mb_ctx* ctx, int n_inters, const mb_inter_t* inters) { MB_CTX_GUARD(ctx); return ctx->e->set_inters(n_inters, inters); }
 int mb_set_exceptions(mb_ctx* ctx, int64_t n_excl, const int32_t* ei, const int32_t* ej, int64_t n_spec, const int32_t* si,
                       const int32_t* sj) {

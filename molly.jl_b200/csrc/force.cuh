@@ -527,7 +527,7 @@ constexpr int AP_THREADS = 128;
 
 template <typename T, int COUL, int CUTM, bool ENERGY>
 __global__ void __launch_bounds__(AP_THREADS)
-    allpairs_force_kernel(int n, PairParams<T> P, T Lx, T Ly, T Lz, const typename VT<T>::T4* __restrict__ posq,
+    allpairs_force_kernel(int n, PairParams<T> P, T Lx, T Ly, T Lz, Tric<T> tric, const typename VT<T>::T4* __restrict__ posq,
                           const typename VT<T>::T2* __restrict__ lj2, const int* __restrict__ ex_ptr,
                           const int* __restrict__ ex_idx, const int* __restrict__ sp_ptr,
                           const int* __restrict__ sp_idx, typename VT<T>::T4* __restrict__ f4,
@@ -564,7 +564,14 @@ __global__ void __launch_bounds__(AP_THREADS)
             T4 pj = s_pos[k];
             T2 lj = s_lj[k];
             // d = c_i - c_j = -vector(c_i, c_j)
-            T dx = -mic_1d(pi.x, pj.x, Lx), dy = -mic_1d(pi.y, pj.y, Ly), dz = -mic_1d(pi.z, pj.z, Lz);
+            T dx, dy, dz;
+            if (tric.on) {  // TriclinicBoundary: dr = vector(c_i, c_j), d = -dr
+                T ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
+                tric_vector<T>(tric, ex, ey, ez);
+                dx = -ex; dy = -ey; dz = -ez;
+            } else {
+                dx = -mic_1d(pi.x, pj.x, Lx); dy = -mic_1d(pi.y, pj.y, Ly); dz = -mic_1d(pi.z, pj.z, Lz);
+            }
             T r2 = dx * dx + dy * dy + dz * dz;
             T fr, e;
             pair_eval_rt<T, COUL, CUTM, ENERGY>(P, r2, li.x, li.y, lj.x, lj.y, kq_i, pj.w, excluded, special, fr, e);

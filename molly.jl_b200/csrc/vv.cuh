@@ -51,7 +51,7 @@ __global__ void ingest_kernel(int n, Geom<T> g, const T* __restrict__ coords, co
     T r[3] = {ref.x, ref.y, ref.z};
     T d2 = (T)0;
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
+    for (int d = 0; d < 3 && !g.tric.on; d++) {  // (triclinic boxes run the no-list path: the caller's coordinates are taken as they are)
         T dd = x[d] - r[d];
         dd -= g.L[d] * frint(dd * g.invL[d]);
         d2 += dd * dd;
@@ -80,12 +80,17 @@ __global__ void export_kernel(int n, Geom<T> g, const typename VT<T>::T4* __rest
     if (coords) {
         typename VT<T>::T4 p = pos4[s];
         T x[3] = {p.x, p.y, p.z};
+        if (g.tric.on) {
+            tric_wrap<T>(g.tric, x[0], x[1], x[2]);
+            for (int d = 0; d < 3; d++) coords[3 * (size_t)o + d] = x[d];
+        } else {
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            T v = x[d] - ffloor(x[d] * g.invL[d]) * g.L[d];
-            if (v >= g.L[d]) v -= g.L[d];
-            if (v < (T)0) v = (T)0;
-            coords[3 * (size_t)o + d] = v;
+            for (int d = 0; d < 3; d++) {
+                T v = x[d] - ffloor(x[d] * g.invL[d]) * g.L[d];
+                if (v >= g.L[d]) v -= g.L[d];
+                if (v < (T)0) v = (T)0;
+                coords[3 * (size_t)o + d] = v;
+            }
         }
     }
     if (vels) {
@@ -104,8 +109,12 @@ __global__ void wrap_kernel(int n, Geom<T> g, typename VT<T>::T4* __restrict__ p
     if (s >= n) return;
     typename VT<T>::T4 p = pos4[s];
     T x[3] = {p.x, p.y, p.z};
+    if (g.tric.on) {
+        tric_wrap<T>(g.tric, x[0], x[1], x[2]);
+    } else {
 #pragma unroll
-    for (int d = 0; d < 3; d++) x[d] = x[d] - ffloor(x[d] / g.L[d]) * g.L[d];  // wrap_coord_1D
+        for (int d = 0; d < 3; d++) x[d] = x[d] - ffloor(x[d] / g.L[d]) * g.L[d];  // wrap_coord_1D
+    }
     p.x = x[0]; p.y = x[1]; p.z = x[2];
     pos4[s] = p;
 }

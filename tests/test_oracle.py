@@ -284,3 +284,31 @@ def test_water3_pme_openmm_literals():
     fx, ex = pme.ewald_exclusion(w["coords"], w["charge"], w["box"], w["excluded"], r_cut=rc)
     assert np.linalg.norm(f + fr + fx - w["forces_pme"], axis=1).max() < 1e-7  # reference: 5e-4
     assert abs(e + er + ex - float(w["energy_pme"])) < 1e-8                   # reference: 2e-4
+
+
+def test_triclinic_oracle_pins():
+    """oracle/triclinic.py against the reference's own checks: basis-vector literals of the lengths + angles constructor
+    (test/basic.jl:130-135), wrap_coords leaves in-box coordinates alone (:219), the approximate minimum image equals the exact
+    27-image search up to half the smallest height (:221-234)."""
+    from oracle import triclinic as tr
+    bv = tr.basis_from_lengths_angles([2.2, 2.0, 1.8], np.deg2rad([50.0, 40.0, 60.0]))
+    lit = np.array([[2.2, 0.0, 0.0], [1.0, 1.7320508, 0.0], [1.37888, 0.5399122, 1.0233204]])
+    assert np.abs(bv - lit).max() < 1e-6
+    t = tr.Triclinic(bv)
+    rng = np.random.default_rng(7)
+    x = rng.random((1000, 3)) @ bv  # fractional coordinates in [0, 1): inside the box
+    assert all(np.array_equal(t.wrap(v), v) or np.abs(t.wrap(v) - v).max() < 1e-12 for v in x)
+    lim = min(bv[0, 0], bv[1, 1], bv[2, 2]) / 2
+    n_checked = 0
+    for i in range(999):
+        de = t.vector_exact(x[i], x[i + 1])
+        if np.linalg.norm(de) <= lim:
+            n_checked += 1
+            assert np.allclose(de, t.vector(x[i], x[i + 1]), atol=1e-12)
+    assert n_checked > 100
+    # out-of-box coordinates come back inside, displaced by lattice vectors only
+    y = x + rng.integers(-2, 3, (1000, 3)) @ bv
+    w = np.array([t.wrap(v) for v in y])
+    assert np.abs(w - x).max() < 1e-9
+    with pytest.raises(ValueError):
+        tr.Triclinic([[2.0, 0.1, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 2.0]])
