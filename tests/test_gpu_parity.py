@@ -772,3 +772,42 @@ def test_triclinic_boundary(dtype):
     # the engine refuses what it does not implement for such a box
     with pytest.raises(ValueError):
         mb.TriclinicBoundary([2.0, 0.1, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 2.0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# energy conservation, the reference's protocol (test/energy_conservation.jl:9-75)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cut", ["distance", "shifted_potential", "shifted_force", "cubic_spline"])
+def test_energy_conservation_reference_protocol(cut):
+    """2 000 atoms (m 40, sigma 0.05, eps 0.2) at 1 K in a 5 nm box, LJ with dist_cutoff 3.0 nm, VelocityVerlet dt 1 fs without
+    CM removal, Float64: max |E(t) - E0| over 10 000 steps (sampled every 100) < 5e-4 kJ/mol, final coordinates inside the box."""
+    n, L, rc = 2000, 5.0, 3.0
+    rng = np.random.default_rng(11)
+    pts = np.empty((0, 3))
+    while len(pts) < n:  # place_atoms(n, boundary; min_dist = 0.1) (src/setup.jl:23-60): rejection sampling, in batches
+        c = rng.random((4 * n, 3)) * L
+        for q in c:
+            d = pts - q
+            d -= L * np.round(d / L)
+            if len(pts) == 0 or (np.einsum("ij,ij->i", d, d) > 0.01).all():
+                pts = np.vstack([pts, q])
+                if len(pts) == n:
+                    break
+    cutoff = {"distance": mb.DistanceCutoff(rc), "shifted_potential": mb.ShiftedPotentialCutoff(rc),
+              "shifted_force": mb.ShiftedForceCutoff(rc), "cubic_spline": mb.CubicSplineCutoff(rc, rc + 0.5)}[cut]
+    mass = np.full(n, 40.0)
+    atoms = mb.atoms_from_arrays(mass, np.zeros(n), np.full(n, 0.05), np.full(n, 0.2), np.float64)
+    v = rng.normal(0.0, np.sqrt(mb.BOLTZMANN_K * 1.0 / 40.0), (n, 3))
+    s = mb.System(atoms=atoms, coords=pts.copy(), boundary=mb.CubicBoundary(L), velocities=v,
+                  pairwise_inters=(mb.LennardJones(cutoff=cutoff, use_neighbors=True),),
+                  neighbor_finder=mb.GPUNeighborFinder(dist_cutoff=rc + (0.5 if cut == "cubic_spline" else 0.0)), dtype=np.float64)
+    sim = mb.VelocityVerlet(dt=0.001, remove_CM_motion=0)
+    e0 = mb.potential_energy(s) + mb.kinetic_energy(s)
+    worst = 0.0
+    for k in range(100):
+        mb.simulate(s, sim, 100, init_step=100 * k)
+        worst = max(worst, abs(mb.potential_energy(s) + mb.kinetic_energy(s) - e0))
+    print(f"[energy conservation, {cut}] path={s.stats()['path']} E0={e0:.6f} max|E-E0| over 10000 steps = {worst:.3e} kJ/mol (bar 5e-4)")
+    assert worst < 5e-4
+    assert (s.coords >= 0).all() and (s.coords < L).all()
+    s.close()

@@ -80,3 +80,27 @@ def test_water3_pme_openmm_literals(dtype, tol_f, tol_e):
     print(f"[water3 {np.dtype(dtype).name}] max|dF| = {err:.3e} dE = {e - float(w['energy_pme']):.3e}")
     assert err < tol_f and abs(e - float(w["energy_pme"])) < tol_e
     s.close()
+
+
+def test_c5_pme_energy_error_is_second_order_f64(golden_6mrr):
+    """BASELINE config 5 on the system the reference ships goldens for (6mrr with :pme, Float64), total
+    energy sampled like test/energy_conservation.jl:61-72. The reference states no bar for a solvated protein, and this start
+    (flexible TIP3P, velocities_300K) does not sit on the integrator's shadow Hamiltonian: E(t) - E0 moves by
+    O(dt^2 sum F^2/m) while the O-H stretches thermalise (-2240 kJ/mol after 1000 steps of 0.5 fs, identical with the
+    reaction-field cutoff instead of PME, with and without CM removal, in one call or in ten - scripts/diag_c5.py; OpenMM's own
+    100-step state, reproduced to 1e-10 nm by the test above, carries the same +85 kJ/mol). What VelocityVerlet guarantees is the
+    ORDER of that error: the same physical time with half the step must show a quarter of it."""
+    g = golden_6mrr
+
+    def drift(dt, n_steps):
+        s = H.sixmrr_pme_system(g, np.float64, exact=True, velocities=g["velocities_300K"])
+        e0 = mb.potential_energy(s) + mb.kinetic_energy(s)
+        mb.simulate(s, mb.VelocityVerlet(dt=dt), n_steps)
+        de = mb.potential_energy(s) + mb.kinetic_energy(s) - e0
+        s.close()
+        return de
+
+    d1 = drift(0.0005, 400)
+    d2 = drift(0.00025, 800)
+    print(f"[C5: 6mrr PME f64 NVE, 0.2 ps] E - E0 = {d1:.3f} kJ/mol at dt 0.5 fs, {d2:.3f} kJ/mol at dt 0.25 fs, ratio {d1 / d2:.2f} (second order: 4)")
+    assert 3.0 < d1 / d2 < 5.0
