@@ -1677,7 +1677,7 @@ class Engine : public EngineBase {
         const bool dec = decomposed() && path_ == 1;
         const int s0 = dec ? own_s0_ : 0, n_own = dec ? own_n_ : (int)n_;
         const int nb = std::max(1, (n_own + 255) / 256);
-        const int vvb = std::max(1, std::min((n_own + VV_THREADS - 1) / VV_THREADS, 8 * sm_count_));  // grid-stride: <= 1184 partials
+        const int vvb = std::max(1, std::min((n_own + 2 * VV_THREADS - 1) / (2 * VV_THREADS), 8 * sm_count_));  // two atoms per thread
         Control* ctl = d_ctl_.as<Control>();
         CmState<T>* cm = d_cm_.as<CmState<T>>();
         // decomposed run over peer memory (peer.cuh): K1 mirrors the boundary slots into the neighbours while it drifts
@@ -1696,7 +1696,7 @@ class Engine : public EngineBase {
         prof_.begin(Prof::VV);
         const Thermo<T> th = thermo_in_k1(c);
         auto k1 = th.on ? vv_kick_drift_kernel<T, true> : vv_kick_drift_kernel<T, false>;
-        k1<<<std::min(nb, 8 * sm_count_), 256, 0, stream_>>>(  // one atom per thread up to 8 resident CTAs per SM
+        k1<<<std::max(1, std::min((nb + 1) / 2, 5 * sm_count_)), 256, 0, stream_>>>(  // two atoms per thread, one wave (48 registers: 5 CTAs per SM)
             s0, n_own, c.dt, c.dt_half, c.skin_half2, cm, d_f4_.as<T4>(), d_xref4_.as<T4>(), d_pos4_.as<T4>(), d_vel4_.as<T4>(),
             c.flag_ptr, ctl, handle, capture && path_ == 1 ? 1 : 0, push, ext_map(), th);
         prof_.end(Prof::VV);
@@ -1742,7 +1742,7 @@ class Engine : public EngineBase {
         }
         const int s0b = dec ? own_s0_ : 0, n_ownb = dec ? own_n_ : (int)n_;  // ownership may have changed in the rebuild
         const int nb2 = std::max(1, (n_ownb + 255) / 256);
-        const int vvb2 = std::max(1, std::min((n_ownb + VV_THREADS - 1) / VV_THREADS, 8 * sm_count_));
+        const int vvb2 = std::max(1, std::min((n_ownb + 2 * VV_THREADS - 1) / (2 * VV_THREADS), 8 * sm_count_));
         if (path_ == 0) MB_TRY(launch_allpairs(false, d_pos4_.as<T4>(), d_lj2_.as<T2>(), d_f4_.as<T4>()));
         else MB_TRY(launch_force(false, dec));
         MB_TRY(launch_bonded(false));

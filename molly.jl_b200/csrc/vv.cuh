@@ -211,33 +211,51 @@ __global__ void vv_kick_drift_kernel(int s0, int n, T dt, T dt_half, T skin_half
     }
     bool moved = false;
     float d2max = 0.f;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int s = s0 + k;  // [s0, s0 + n): the slots this rank owns
-        typename VT<T>::T4 v = vel4[s];
-        const typename VT<T>::T4 f = f4[s];
-        typename VT<T>::T4 p = pos4[s];
-        const typename VT<T>::T4 r = xref4[s];
-        // map into the extended array, requested together with the state so that no load waits behind the arithmetic
-        int e_own = 0;
-        unsigned int e_gp = 0;
-        if (ext.pos4e) { e_own = ext.ext_of[s]; e_gp = ext.gptr[s]; }
-        if (cmv) { v.x -= cx; v.y -= cy; v.z -= cz; }
-        if (THERMO && thermo) andersen_apply<T>(v, th.orig[s], th.n, th.mass[s], th.kT, th.prob, t_step, t_c0, t_c1, t_k0, t_k1);
-        const T a = v.w * dt_half;  // (1/m) dt/2
-        v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
-        p.x += v.x * dt; p.y += v.y * dt; p.z += v.z * dt;
-        vel4[s] = v;
-        pos4[s] = p;
-        if (ext.pos4e) {
-            // extended (ghost-padded) array the force kernel stages from: own entry + periodic-image copies
-            ext_store_at<T>(ext, e_own, e_gp, p, ext.pos4e);
-            for (int q = 0; q < push.n_seg; q++)  // halo exchange fused into the drift: mirror boundary slots into the peers
-                if ((unsigned int)(s - push.start[q]) < (unsigned int)push.count[q]) ext_store_at<T>(ext, e_own, e_gp, p, push.dst[q]);
+    // Two atoms per thread and iteration, all loads of both requested before any arithmetic: the kernel is bound by memory
+    // latency (one wave of CTAs, ~130 B per atom), so the second atom's round trip hides behind the first one's.
+    constexpr int UNR = 2;
+    const int stride = gridDim.x * blockDim.x;
+    for (int k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < n; k0 += UNR * stride) {
+        typename VT<T>::T4 v[UNR], f[UNR], p[UNR], r[UNR];
+        int e_own[UNR];
+        unsigned int e_gp[UNR];
+        bool ok[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const int k = k0 + u * stride;
+            ok[u] = k < n;
+            const int s = s0 + (ok[u] ? k : k0);  // [s0, s0 + n): the slots this rank owns
+            v[u] = vel4[s];
+            f[u] = f4[s];
+            p[u] = pos4[s];
+            r[u] = xref4[s];
+            // map into the extended array, requested together with the state so that no load waits behind the arithmetic
+            e_own[u] = 0;
+            e_gp[u] = 0;
+            if (ext.pos4e) { e_own[u] = ext.ext_of[s]; e_gp[u] = ext.gptr[s]; }
         }
-        const T dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
-        const T d2 = dx * dx + dy * dy + dz * dz;
-        moved |= (d2 > skin_half2);
-        d2max = fmaxf(d2max, (float)d2);
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            if (!ok[u]) continue;
+            const int s = s0 + k0 + u * stride;
+            if (cmv) { v[u].x -= cx; v[u].y -= cy; v[u].z -= cz; }
+            if (THERMO && thermo) andersen_apply<T>(v[u], th.orig[s], th.n, th.mass[s], th.kT, th.prob, t_step, t_c0, t_c1, t_k0, t_k1);
+            const T a = v[u].w * dt_half;  // (1/m) dt/2
+            v[u].x += f[u].x * a; v[u].y += f[u].y * a; v[u].z += f[u].z * a;
+            p[u].x += v[u].x * dt; p[u].y += v[u].y * dt; p[u].z += v[u].z * dt;
+            vel4[s] = v[u];
+            pos4[s] = p[u];
+            if (ext.pos4e) {
+                // extended (ghost-padded) array the force kernel stages from: own entry + periodic-image copies
+                ext_store_at<T>(ext, e_own[u], e_gp[u], p[u], ext.pos4e);
+                for (int q = 0; q < push.n_seg; q++)  // halo exchange fused into the drift: mirror boundary slots into the peers
+                    if ((unsigned int)(s - push.start[q]) < (unsigned int)push.count[q]) ext_store_at<T>(ext, e_own[u], e_gp[u], p[u], push.dst[q]);
+            }
+            const T dx = p[u].x - r[u].x, dy = p[u].y - r[u].y, dz = p[u].z - r[u].z;
+            const T d2 = dx * dx + dy * dy + dz * dz;
+            moved |= (d2 > skin_half2);
+            d2max = fmaxf(d2max, (float)d2);
+        }
     }
     if (moved) *flag = 1;
     for (int o = 16; o > 0; o >>= 1) d2max = fmaxf(d2max, __shfl_xor_sync(0xffffffffu, d2max, o));
@@ -283,15 +301,26 @@ __global__ void __launch_bounds__(VV_THREADS)
                     Control* __restrict__ ctl, CmState<T>* __restrict__ cm, int apply_pending, double* __restrict__ mom_out,
                     PeerSignal sig) {
     double px = 0, py = 0, pz = 0;
-    for (int s = s0 + blockIdx.x * blockDim.x + threadIdx.x; s < s0 + n; s += gridDim.x * blockDim.x) {
-        typename VT<T>::T4 v = vel4[s];
-        if (apply_pending && cm->valid) { v.x -= cm->v[0]; v.y -= cm->v[1]; v.z -= cm->v[2]; }
-        const typename VT<T>::T4 f = f4[s];
-        const T a = v.w * dt_half;
-        v.x += f.x * a; v.y += f.y * a; v.z += f.z * a;
-        vel4[s] = v;
-        const T m = mass[s];
-        px += (double)(v.x * m); py += (double)(v.y * m); pz += (double)(v.z * m);
+    const int stride = gridDim.x * blockDim.x;
+    for (int sa = s0 + blockIdx.x * blockDim.x + threadIdx.x; sa < s0 + n; sa += 2 * stride) {  // two atoms in flight per thread
+        const int sb = sa + stride;
+        const bool okb = sb < s0 + n;
+        typename VT<T>::T4 va = vel4[sa], vb = vel4[okb ? sb : sa];
+        const typename VT<T>::T4 fa = f4[sa], fb = f4[okb ? sb : sa];
+        const T ma = mass[sa], mb_ = mass[okb ? sb : sa];
+        if (apply_pending && cm->valid) {
+            va.x -= cm->v[0]; va.y -= cm->v[1]; va.z -= cm->v[2];
+            vb.x -= cm->v[0]; vb.y -= cm->v[1]; vb.z -= cm->v[2];
+        }
+        const T aa = va.w * dt_half, ab = vb.w * dt_half;
+        va.x += fa.x * aa; va.y += fa.y * aa; va.z += fa.z * aa;
+        vb.x += fb.x * ab; vb.y += fb.y * ab; vb.z += fb.z * ab;
+        vel4[sa] = va;
+        px += (double)(va.x * ma); py += (double)(va.y * ma); pz += (double)(va.z * ma);
+        if (okb) {
+            vel4[sb] = vb;
+            px += (double)(vb.x * mb_); py += (double)(vb.y * mb_); pz += (double)(vb.z * mb_);
+        }
     }
     if (!do_cm && sig.n_peer == 0) return;
     __shared__ double s_red[VV_THREADS / 32][3];
