@@ -15,8 +15,12 @@ rc 1.2 nm, Float32 (FCC + jitter, 90 K, dt 2 fs).
           read x 12 + params 12 + write F 12) / mean launch time measured with CUDA events by the
           library's stage timers; peak = MEASURED_PEAKS.json hbm_gbs. The FP32-ALU fraction that actually
           binds this kernel is reported beside it (`fp32`).
-  cpu_baseline  the oracle's restatement of Molly's multithreaded CPU algorithm (cell list every 10 steps,
-          +0.2 nm buffer, per-thread force copies) on the same workload, bounded sample.
+  cpu_baseline  the oracle's restatement of Molly's multithreaded CPU algorithm (threaded cell list every 10 steps with
+          the GPU arm's list radius, threaded pair loop with per-thread force copies) on the same workload, bounded sample.
+  workloads  (default run only) the other configurations BASELINE.json names, shorter runs, same fields: c3 = 6mrr
+          (replicas when N > 1: its box does not shard), c4 = 1M-atom LJ fluid (decomposed like c2 when N > 1).
+  N > 1   spatial decomposition of ONE system (strong scaling); roofline / fp32 use the per-rank share of bytes and pairs
+          and the slowest rank's kernel time.
 
 --impl reference times that CPU restatement alone (Julia is not installed, so Molly.jl itself cannot run;
 kind = "port").
