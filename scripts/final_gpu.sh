@@ -3,7 +3,7 @@
 # ncu reports stay in /tmp on the box (gpurun_out/ is limited to 64 MiB); only the csv pages come back.
 R=${1:-r02}
 mkdir -p gpurun_out
-python -m pytest tests -x -q -m gpu -s 2>&1 | grep -E "^\[|passed|failed|error" | tail -60 > gpurun_out/${R}_gputests.log; tail -3 gpurun_out/${R}_gputests.log
+python -m pytest tests -x -q -m gpu -s 2>&1 | grep -E "\[|passed|failed|error" | tail -60 > gpurun_out/${R}_gputests.log; tail -3 gpurun_out/${R}_gputests.log
 python __graft_entry__.py --smoke 2>&1 | tail -2
 python bench.py 2>gpurun_out/${R}_bench.err | tail -1 > gpurun_out/${R}_bench_c2.json
 python bench.py --impl reference --steps 10 --warmup 1 2>/dev/null | tail -1 > gpurun_out/${R}_bench_c2_reference_arm.json
