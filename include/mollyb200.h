@@ -85,7 +85,7 @@ typedef struct {
     int64_t force_launches, vv_launches, rebuild_launches;
     int32_t graph_mode;        /* last mb_simulate_vv: 1 = CUDA-graph step with conditional rebuild node,
                                 * 0 = stream launches, -1 = graph construction failed (stream launches) */
-    int32_t n_prunes;          /* dual-list: refreshes of the inner (pruned) lists */
+    int32_t n_prunes;          /* always 0 (field kept for ABI stability: the dual-list experiment of round 1 was removed) */
     int32_t peer_transport;    /* decomposed runs: 1 = halo exchange and sum(m v) over NVLink peer memory (IPC-mapped
                                 * stores fused into the drift / kick kernels), 0 = NCCL send/recv + all-reduce */
     int32_t reserved_;         /* decomposed runs: the rebuild interval the next call will use (adapted from displacements) */
