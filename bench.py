@@ -130,6 +130,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def default_r_list(wl, rc):
+    """List radius = cutoff + skin. The skins are tuned on B200 (profiles/r02_experiments.md section 8): 0.08 nm for C2 (a rebuild every
+    ~36 steps), 0.10 nm for C4 (its rebuild costs 4x as much), 0.12 nm for 6mrr at 300 K / 0.5 fs. Both arms use the same radius."""
+    return rc + {"c2": 0.08, "c3": 0.12, "c4": 0.10}.get(wl, 0.10)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -154,7 +160,7 @@ def run_cpu(sd, ointers, dt, rc, steps, warmup, dtype=np.float32, r_list=None):
     """Molly-algorithm CPU restatement (oracle): threaded cell list every 10 steps (the reference's find_neighbors policy,
     src/neighbors.jl:671) with the GPU arm's list radius, threaded pair loop, all host threads."""
     if r_list is None:
-        r_list = rc + (0.12 if "golden" in sd else 0.1)
+        r_list = rc + (0.12 if "golden" in sd else 0.10)
     from oracle import oracle as o
     if "golden" in sd:  # 6mrr: pairwise in C (threaded), bonded terms in numpy, f64
         try:
@@ -227,7 +233,7 @@ def main():
         steps = min(steps, 20 if wl == "c2" else (10 if wl == "c4" else 60))  # bounded sample ...
         steps = 10 * max(1, steps // 10)  # ... of whole neighbour-list periods (Molly's default: find_neighbors every 10 steps)
         warm = min(args.warmup if args.warmup is not None else 1, 2)
-        r_list = args.r_list if args.r_list is not None else (rc + 0.1 if wl != "c3" else rc + 0.12)
+        r_list = args.r_list if args.r_list is not None else default_r_list(wl, rc)
         sps, nt, t = run_cpu(sd, ointers, dt, rc, steps, warm, r_list=r_list)
         out = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
                "warmup": warm, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -280,7 +286,7 @@ def run_ours(wl, args, ctx, steps, warmup, with_cpu, with_e2e, brief=False):
     dtype = np.float32
     sd, inters, ointers, dt, rc, label = workload(wl, dtype)
     n = int(sd["n"])
-    r_list = args.r_list if args.r_list is not None else (rc + 0.1 if wl != "c3" else rc + 0.12)
+    r_list = args.r_list if args.r_list is not None else default_r_list(wl, rc)
 
     atoms = mb.atoms_from_arrays(sd["mass"], sd["charge"], sd["sigma"], sd["eps"], dtype)
     nf = mb.GPUNeighborFinder(dist_cutoff=r_list, excluded_pairs=sd.get("excluded", np.zeros((0, 2), np.int32)) + 1,
